@@ -1,0 +1,811 @@
+// K4/K5: box decoding, candidate selection and class-wise NMS
+// (utils.regression_postprocess utils.py:108-117, boxes_decode 183-195, merge_boxes_decoded
+// 223-227, nms 213-220, nms_classwise 198-210).
+//
+//   select   : streams the [rows, C] scores once; a group of LPR lanes owns a row, keeps its
+//              slice in registers, reduces (max, first argmax) with shuffles and appends the rare
+//              rows with score > thr to the image's candidate list (one atomic per candidate).
+//   finalize : one CTA per image sorts the (unordered) candidates by anchor index -> the
+//              reference's row-major / level-major order, applies the optional per-level top-k,
+//              decodes or gathers the boxes.
+//   nms      : one CTA per image sorts by (class asc, score desc, index asc); one warp per
+//              (image, class) runs the greedy pass -- 32 candidates at a time against the kept
+//              boxes staged in shared memory, then resolves the 32 among themselves with
+//              __ballot_sync masks; one CTA per image compacts class-major.
+#include "rn_common.cuh"
+#include "rn_tiles.cuh"
+
+namespace rn {
+
+constexpr int kSortSmemElems = 16384;  // elements a CTA sorts in shared memory (12 B each)
+constexpr int kSortThreads = 1024;
+
+__device__ __forceinline__ unsigned next_pow2(unsigned v) {
+  unsigned p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// float -> unsigned whose ascending order is the float's ascending order
+__device__ __forceinline__ unsigned sortable_bits(float f) {
+  const unsigned b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+// CTA-wide bitonic sort of (key, pos) pairs, ascending, lexicographic.  n_pad is a power of two;
+// padding entries must hold the maximum key.  Works on shared or global memory.
+__device__ void bitonic_sort_pairs(unsigned long long* key, unsigned* pos, unsigned n_pad) {
+  for (unsigned k = 2; k <= n_pad; k <<= 1) {
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        const unsigned ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long ka = key[i], kb = key[ixj];
+          const unsigned pa = pos[i], pb = pos[ixj];
+          const bool gt = ka > kb || (ka == kb && pa > pb);
+          const bool up = (i & k) == 0;
+          if (gt == up) {
+            key[i] = kb; key[ixj] = ka;
+            pos[i] = pb; pos[ixj] = pa;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- utils.regression_postprocess for one anchor ------------------------------------------------
+__device__ __forceinline__ float4 decode_one(const rn_level_t& L, int y, int x, int a, float4 d) {
+  const float sy = fmul(d.x, L.anchor_h[a]);          // scale_regression, utils.py:100-105
+  const float sx = fmul(d.y, L.anchor_w[a]);
+  const float sh = fmul(expf(d.z), L.anchor_h[a]);    // exp on sizes, utils.py:110-111
+  const float sw = fmul(expf(d.w), L.anchor_w[a]);
+  const float cy = fadd(sy, cell_centre(L.y0, L.y_step, y));  // utils.py:24-36
+  const float cx = fadd(sx, cell_centre(L.x0, L.x_step, x));
+  const float hh = sh * 0.5f, hw = sw * 0.5f;         // utils.py:39-44
+  return make_float4(fsub(cy, hh), fsub(cx, hw), fadd(cy, hh), fadd(cx, hw));
+}
+
+// One kernel for every elementwise box-map op of utils.py / dataset.py (selected by `op`).
+__global__ void boxmap_op_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, int op,
+                                 const __grid_constant__ Ptrs in, const __grid_constant__ Ptrs out) {
+  const long long total = pyr.anchors_per_image * (long long)batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int l = 0;
+    for (int k = 1; k < pyr.num_levels; ++k) l += (i >= pyr.level[k].anchor_offset * batch) ? 1 : 0;
+    const rn_level_t& L = pyr.level[l];
+    const long long local = i - L.anchor_offset * batch;
+    const int a = (int)(local % L.num_anchors);
+    const long long cell = local / L.num_anchors;
+    const int x = (int)(cell % L.grid_w);
+    const int y = (int)((cell / L.grid_w) % L.grid_h);
+    const float4 d = __ldcs(reinterpret_cast<const float4*>(in.p[l]) + local);
+    float4 r;
+    switch (op) {
+      case RN_BOXOP_DECODE:  // utils.regression_postprocess, utils.py:108-117
+        r = decode_one(L, y, x, a, d);
+        break;
+      case RN_BOXOP_ADD_CENTRE:  // utils.boxmap_anchor_relative_to_image_relative, utils.py:22-36
+        r = make_float4(fadd(d.x, cell_centre(L.y0, L.y_step, y)), fadd(d.y, cell_centre(L.x0, L.x_step, x)), d.z, d.w);
+        break;
+      case RN_BOXOP_SCALE:  // utils.scale_regression, utils.py:100-105
+        r = make_float4(fmul(d.x, L.anchor_h[a]), fmul(d.y, L.anchor_w[a]), fmul(d.z, L.anchor_h[a]),
+                        fmul(d.w, L.anchor_w[a]));
+        break;
+      case RN_BOXOP_CENTRE_TO_CORNER: {  // utils.py:39-44, dataset.from_center_box dataset.py:35-39
+        const float hh = d.z * 0.5f, hw = d.w * 0.5f;
+        r = make_float4(fsub(d.x, hh), fsub(d.y, hw), fadd(d.x, hh), fadd(d.y, hw));
+        break;
+      }
+      default: {  // RN_BOXOP_CORNER_TO_CENTRE: dataset.to_center_box, dataset.py:28-32
+        const float sh = fsub(d.z, d.x), sw = fsub(d.w, d.y);
+        r = make_float4(fadd(d.x, sh * 0.5f), fadd(d.y, sw * 0.5f), sh, sw);
+        break;
+      }
+    }
+    __stcs(reinterpret_cast<float4*>(out.p[l]) + local, r);
+  }
+}
+
+// utils.classmap_decode (utils.py:171-179): fg = max_c classmap > thr, one thread per row.
+__global__ void classmap_fg_kernel(long long rows, int C, const float* __restrict__ in, float thr,
+                                   unsigned char* __restrict__ out) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, in[r * C + c]);
+    out[r] = mx > thr;
+  }
+}
+
+// ---- select -----------------------------------------------------------------------------------------
+struct SelectParams {
+  Ptrs scores;
+  int num_classes;
+  int units_per_row;     // C / VEC
+  int images;
+  int capacity;
+  float thr;
+  int is_logits;
+  int32_t* ws_anchor;    // [B, capacity] unordered
+  float* ws_score;
+  int32_t* ws_class;
+  int32_t* count;        // [B]
+  uint32_t* status;
+};
+
+template <int LPR, int VEC, int UPL>
+__global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Segs segs,
+                                                     const __grid_constant__ SelectParams prm) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;                          // lane within the row group
+  const long long group = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / LPR;
+  const long long num_groups = (long long)gridDim.x * blockDim.x / LPR;
+  const long long total_rows = segs.start[RN_MAX_LEVELS];
+  const int C = prm.num_classes;
+  const int upr = prm.units_per_row;
+  // every lane of a warp runs the same number of iterations (shuffles below are full-warp)
+  const long long iters = (total_rows + num_groups - 1) / num_groups;
+  unsigned flags = 0;
+
+  for (long long it = 0; it < iters; ++it) {
+    const long long r = group + it * num_groups;
+    const bool row_ok = r < total_rows;
+    int s = 0;
+    long long rl = 0;
+    const float* base = nullptr;
+    if (row_ok) {
+      s = seg_of(segs, r);
+      rl = r - segs.start[s];
+      base = reinterpret_cast<const float*>(prm.scores.p[s]) + rl * C;
+    }
+    float v[UPL][VEC];
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+      const int u = sub + j * LPR;
+      if (row_ok && u < upr) {
+        if constexpr (VEC == 4) {
+          const float4 t = ld_stream4(base + u * 4);
+          v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+        } else {
+          v[j][0] = __ldcs(base + u);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[j][k] = -INFINITY;
+      }
+    }
+    // (max, first argmax) over this lane's slice, then over the group
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < UPL; ++j) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const int c = (sub + j * LPR) * VEC + k;
+        if (v[j][k] > best) {  // ascending c within a lane: strict '>' keeps the first maximum
+          best = v[j][k];
+          besti = c;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) {
+        best = ob;
+        besti = oi;
+      }
+    }
+    float score = best;
+    int cls = besti;
+    bool fire;
+    if (prm.is_logits) {
+      // The reference takes max/argmax of sigmoid(x) (utils.py:185-186,249).  sigmoid is
+      // monotone up to rounding, so only logits within a rounding window of the max can tie
+      // or win in probability space: evaluate sigmoid for exactly those.
+      const float pmax = sigmoid_f32(best);
+      fire = row_ok && pmax > prm.thr - 4e-7f;
+      if (__any_sync(0xffffffffu, fire)) {
+        const float pq = pmax * (1.0f - pmax);
+        const float lo = pq > 0.f ? best - (2.5e-7f / pq + 1e-6f) : -INFINITY;
+        float bp = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < UPL; ++j) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            if (fire && v[j][k] >= lo) {
+              const float p = sigmoid_f32(v[j][k]);
+              const int c = (sub + j * LPR) * VEC + k;
+              if (p > bp) {
+                bp = p;
+                bi = c;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int o = LPR >> 1; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, bp, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > bp || (ob == bp && oi < bi)) {
+            bp = ob;
+            bi = oi;
+          }
+        }
+        score = bp;
+        cls = bi;
+      }
+      fire = fire && score > prm.thr;
+    } else {
+      fire = row_ok && score > prm.thr;  // strict, utils.py:187
+    }
+    if (fire && sub == 0) {
+      const long long per_image = segs.rows[s] / prm.images;
+      const int b = (int)(rl / per_image);
+      const int anchor = (int)(segs.start[s] / prm.images + (rl - (long long)b * per_image));
+      const int slot = atomicAdd(prm.count + b, 1);
+      if (slot < prm.capacity) {
+        const size_t o = (size_t)b * prm.capacity + slot;
+        prm.ws_anchor[o] = anchor;
+        prm.ws_score[o] = score;
+        prm.ws_class[o] = cls;
+      } else {
+        flags |= RN_FLAG_CAND_OVERFLOW;
+      }
+    }
+  }
+  if (prm.status) {
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (lane == 0 && flags) atomicOr(prm.status, flags);
+  }
+}
+
+// ---- finalize: order candidates, optional per-level top-k, boxes ---------------------------------
+struct FinalizeParams {
+  Ptrs regs;
+  int regs_are_deltas;
+  int capacity;
+  int topk;
+  const int32_t* ws_anchor;
+  const float* ws_score;
+  const int32_t* ws_class;
+  unsigned long long* g_key;  // [B, pad] global sort buffers (used when the list exceeds smem)
+  unsigned* g_pos;
+  unsigned pad;               // next_pow2(capacity)
+  float4* out_boxes;
+  float* out_scores;
+  int32_t* out_classes;
+  int32_t* out_anchor;
+  int32_t* count;             // in: appended, out: final
+};
+
+__global__ void __launch_bounds__(kSortThreads)
+cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const __grid_constant__ FinalizeParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_cnt;
+  const int b = blockIdx.x;
+  const int n = min(prm.count[b], prm.capacity);
+  const size_t base = (size_t)b * prm.capacity;
+  const unsigned n_pad = max(next_pow2((unsigned)n), 2u);
+  unsigned long long* key;
+  unsigned* pos;
+  if (n_pad <= (unsigned)kSortSmemElems) {
+    key = reinterpret_cast<unsigned long long*>(smem_raw);
+    pos = reinterpret_cast<unsigned*>(key + n_pad);
+  } else {
+    key = prm.g_key + (size_t)b * prm.pad;
+    pos = prm.g_pos + (size_t)b * prm.pad;
+  }
+  // 1) ascending anchor index == the reference's (level, y, x, a) order
+  for (unsigned i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    key[i] = i < (unsigned)n ? (unsigned long long)(unsigned)prm.ws_anchor[base + i] : ~0ull;
+    pos[i] = i;
+  }
+  __syncthreads();
+  bitonic_sort_pairs(key, pos, n_pad);
+
+  int n_final = n;
+  if (prm.topk > 0) {
+    // 2) per-level top-k (extension, not in the reference): within each level's contiguous range
+    // sort by (score desc, anchor asc), drop everything past k, then restore anchor order.
+    bool any = false;
+    for (int l = 0; l < pyr.num_levels; ++l) {
+      const unsigned lo_a = (unsigned)pyr.level[l].anchor_offset;
+      const unsigned hi_a = l + 1 < pyr.num_levels ? (unsigned)pyr.level[l + 1].anchor_offset
+                                                   : (unsigned)pyr.anchors_per_image;
+      // range of this level in the sorted list (uniform across the CTA: every thread searches)
+      int lo = 0, hi = n;
+      while (lo < hi) { const int m = (lo + hi) >> 1; if ((unsigned)key[m] < lo_a) lo = m + 1; else hi = m; }
+      const int start = lo;
+      hi = n;
+      while (lo < hi) { const int m = (lo + hi) >> 1; if ((unsigned)key[m] < hi_a) lo = m + 1; else hi = m; }
+      const int end = lo;
+      if (end - start <= prm.topk) continue;
+      any = true;
+      __syncthreads();
+      // rank of element i within the level by (score desc, anchor asc); O(m^2 / threads), rare path
+      for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
+        const float si = prm.ws_score[base + pos[i]];
+        int rank = 0;
+        for (int j = start; j < end; ++j) {
+          const float sj = prm.ws_score[base + pos[j]];
+          rank += (sj > si) || (sj == si && j < i);
+        }
+        if (rank >= prm.topk) key[i] |= 1ull << 63;  // mark dropped: sorts behind every kept entry
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (any) {
+      bitonic_sort_pairs(key, pos, n_pad);
+      if (threadIdx.x == 0) s_cnt = 0;
+      __syncthreads();
+      int c = 0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) c += (key[i] >> 63) == 0;
+      c = warp_sum(c);
+      if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+      __syncthreads();
+      n_final = s_cnt;
+    }
+  }
+  // 3) outputs
+  for (int i = threadIdx.x; i < n_final; i += blockDim.x) {
+    const unsigned p = pos[i];
+    const int anchor = prm.ws_anchor[base + p];
+    prm.out_scores[base + i] = prm.ws_score[base + p];
+    prm.out_classes[base + i] = prm.ws_class[base + p];
+    prm.out_anchor[base + i] = anchor;
+    int l = 0;
+    for (int k = 1; k < pyr.num_levels; ++k) l += (anchor >= pyr.level[k].anchor_offset) ? 1 : 0;
+    const rn_level_t& L = pyr.level[l];
+    const int local = anchor - (int)L.anchor_offset;
+    const long long rl = (long long)b * L.grid_h * L.grid_w * L.num_anchors + local;
+    float4 d = __ldg(reinterpret_cast<const float4*>(prm.regs.p[l]) + rl);
+    if (prm.regs_are_deltas) {
+      const int a = local % L.num_anchors;
+      const int cell = local / L.num_anchors;
+      d = decode_one(L, cell / L.grid_w, cell % L.grid_w, a, d);
+    }
+    prm.out_boxes[base + i] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) prm.count[b] = n_final;
+}
+
+// ---- NMS ------------------------------------------------------------------------------------------
+struct NmsParams {
+  int batch, num_classes, capacity, out_capacity, max_out;
+  float iou_thr;
+  const float4* boxes;
+  const float* scores;
+  const int32_t* classes;
+  const int32_t* count;
+  unsigned long long* g_key;
+  unsigned* g_pos;
+  unsigned pad;
+  unsigned* perm;       // [B, capacity] candidate index by sorted rank
+  int32_t* seg;         // [B, C + 1] class segment starts in sorted order
+  unsigned* kept;       // [B, capacity] sorted ranks kept, stored at seg start + j
+  int32_t* kept_count;  // [B, C]
+  float4* det_boxes;
+  float* det_scores;
+  int32_t* det_classes;
+  int32_t* det_index;
+  int32_t* det_count;
+  uint32_t* status;
+  int kept_cap;         // kept boxes a warp can stage in shared memory
+};
+
+__global__ void __launch_bounds__(kSortThreads) nms_sort_kernel(const __grid_constant__ NmsParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int n = min(max(prm.count[b], 0), prm.capacity);
+  const size_t base = (size_t)b * prm.capacity;
+  const unsigned n_pad = max(next_pow2((unsigned)n), 2u);
+  unsigned long long* key;
+  unsigned* pos;
+  if (n_pad <= (unsigned)kSortSmemElems) {
+    key = reinterpret_cast<unsigned long long*>(smem_raw);
+    pos = reinterpret_cast<unsigned*>(key + n_pad);
+  } else {
+    key = prm.g_key + (size_t)b * prm.pad;
+    pos = prm.g_pos + (size_t)b * prm.pad;
+  }
+  for (unsigned i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    if (i < (unsigned)n) {
+      const unsigned c = (unsigned)prm.classes[base + i];
+      const unsigned s = ~sortable_bits(prm.scores[base + i]);  // descending score
+      key[i] = ((unsigned long long)c << 32) | s;
+    } else {
+      key[i] = ~0ull;
+    }
+    pos[i] = i;  // ties -> lower candidate index first (stable order of tf.image.non_max_suppression)
+  }
+  __syncthreads();
+  bitonic_sort_pairs(key, pos, n_pad);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) prm.perm[base + i] = pos[i];
+  // class c starts at the first sorted rank whose class >= c
+  for (int c = threadIdx.x; c <= prm.num_classes; c += blockDim.x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if ((unsigned)(key[m] >> 32) < (unsigned)c) lo = m + 1; else hi = m;
+    }
+    prm.seg[(size_t)b * (prm.num_classes + 1) + c] = lo;
+  }
+}
+
+struct NmsBox {
+  float y0, x0, y1, x1, area;
+};
+
+// Box normalisation and area exactly as TF's CPU NonMaxSuppression kernel does it.
+__device__ __forceinline__ NmsBox nms_box(float4 r) {
+  NmsBox q;
+  q.y0 = fminf(r.x, r.z); q.x0 = fminf(r.y, r.w);
+  q.y1 = fmaxf(r.x, r.z); q.x1 = fmaxf(r.y, r.w);
+  q.area = fmul(fsub(q.y1, q.y0), fsub(q.x1, q.x0));
+  return q;
+}
+
+__device__ __forceinline__ bool nms_suppresses(const NmsBox& a, const NmsBox& b, float thr) {
+  if (a.area <= 0.f || b.area <= 0.f) return false;
+  const float iy0 = fmaxf(a.y0, b.y0), ix0 = fmaxf(a.x0, b.x0);
+  const float iy1 = fminf(a.y1, b.y1), ix1 = fminf(a.x1, b.x1);
+  const float inter = fmul(fmaxf(fsub(iy1, iy0), 0.f), fmaxf(fsub(ix1, ix0), 0.f));
+  const float iou = fdiv(inter, fsub(fadd(a.area, b.area), inter));
+  return iou > thr;
+}
+
+constexpr int kNmsWarps = 4;
+
+__global__ void __launch_bounds__(kNmsWarps * 32) nms_greedy_kernel(const __grid_constant__ NmsParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * kNmsWarps + warp;   // (image, class) pair
+  if (w >= (long long)prm.batch * prm.num_classes) return;  // whole warp leaves together
+  const int b = (int)(w / prm.num_classes);
+  const int c = (int)(w % prm.num_classes);
+  NmsBox* s_kept = reinterpret_cast<NmsBox*>(smem_raw) + (size_t)warp * prm.kept_cap;
+  const int* seg = prm.seg + (size_t)b * (prm.num_classes + 1);
+  const int start = seg[c], end = seg[c + 1];
+  const size_t base = (size_t)b * prm.capacity;
+  int n_kept = 0;
+  for (int chunk = start; chunk < end && n_kept < prm.max_out; chunk += 32) {
+    const int i = chunk + lane;
+    const bool valid = i < end;
+    NmsBox me = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) me = nms_box(__ldg(prm.boxes + base + prm.perm[base + i]));
+    bool alive = valid;
+    // against boxes kept by earlier chunks
+    for (int k = 0; k < n_kept && __any_sync(0xffffffffu, alive); ++k) {
+      if (alive && nms_suppresses(me, s_kept[k], prm.iou_thr)) alive = false;
+    }
+    // among the 32 of this chunk, in score order
+    unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+    for (int t = 0; t < 32; ++t) {
+      if (!((alive_mask >> t) & 1u)) continue;  // uniform: alive_mask is warp-wide
+      if (n_kept >= prm.max_out) {
+        alive_mask &= (1u << t) - 1u;           // output full: drop t and everything after it
+        break;
+      }
+      NmsBox kb;
+      kb.y0 = __shfl_sync(0xffffffffu, me.y0, t);
+      kb.x0 = __shfl_sync(0xffffffffu, me.x0, t);
+      kb.y1 = __shfl_sync(0xffffffffu, me.y1, t);
+      kb.x1 = __shfl_sync(0xffffffffu, me.x1, t);
+      kb.area = __shfl_sync(0xffffffffu, me.area, t);
+      if (lane == 0) {
+        s_kept[n_kept] = kb;
+        prm.kept[base + start + n_kept] = (unsigned)(chunk + t);
+      }
+      ++n_kept;
+      const bool dies = lane > t && ((alive_mask >> lane) & 1u) && nms_suppresses(me, kb, prm.iou_thr);
+      alive_mask &= ~__ballot_sync(0xffffffffu, dies);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) prm.kept_count[(size_t)b * prm.num_classes + c] = n_kept;
+}
+
+__global__ void __launch_bounds__(256) nms_compact_kernel(const __grid_constant__ NmsParams prm) {
+  __shared__ int s_off[1025];
+  const int b = blockIdx.x;
+  const int C = prm.num_classes;
+  const int* kc = prm.kept_count + (size_t)b * C;
+  const int* seg = prm.seg + (size_t)b * (C + 1);
+  const size_t base = (size_t)b * prm.capacity;
+  const size_t obase = (size_t)b * prm.out_capacity;
+  // exclusive prefix over classes (C is small; chunked serial scan by thread 0)
+  __shared__ int s_total;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += 1024) {
+    const int cn = min(1024, C - c0);
+    if (threadIdx.x == 0) {
+      int acc = s_total;
+      for (int c = 0; c < cn; ++c) {
+        s_off[c] = acc;
+        acc += kc[c0 + c];
+      }
+      s_off[cn] = acc;
+    }
+    __syncthreads();
+    for (int c = 0; c < cn; ++c) {
+      const int off = s_off[c], m = s_off[c + 1] - s_off[c];
+      const int st = seg[c0 + c];
+      for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int o = off + j;
+        if (o < prm.out_capacity) {
+          const unsigned rank = prm.kept[base + st + j];
+          const unsigned ci = prm.perm[base + rank];
+          prm.det_boxes[obase + o] = prm.boxes[base + ci];
+          prm.det_scores[obase + o] = prm.scores[base + ci];
+          prm.det_classes[obase + o] = prm.classes[base + ci];
+          prm.det_index[obase + o] = (int)ci;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_total = s_off[cn];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int tot = s_total;
+    if (tot > prm.out_capacity) {
+      tot = prm.out_capacity;
+      if (prm.status) atomicOr(prm.status, RN_FLAG_DET_OVERFLOW);
+    }
+    prm.det_count[b] = tot;
+  }
+}
+
+static unsigned host_next_pow2(unsigned v) {
+  unsigned p = 2;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t sort_smem_bytes(int capacity) {
+  unsigned pad = host_next_pow2((unsigned)capacity);
+  if (pad > (unsigned)kSortSmemElems) pad = kSortSmemElems;
+  return (size_t)pad * 12;
+}
+
+static bool needs_global_sort(int capacity) { return host_next_pow2((unsigned)capacity) > (unsigned)kSortSmemElems; }
+
+template <int LPR, int VEC>
+static void launch_select(int upl, unsigned grid, cudaStream_t st, const Segs& segs, const SelectParams& prm) {
+  switch (upl) {
+    case 1: select_kernel<LPR, VEC, 1><<<grid, 256, 0, st>>>(segs, prm); break;
+    case 2: select_kernel<LPR, VEC, 2><<<grid, 256, 0, st>>>(segs, prm); break;
+    case 3: select_kernel<LPR, VEC, 3><<<grid, 256, 0, st>>>(segs, prm); break;
+    case 4: select_kernel<LPR, VEC, 4><<<grid, 256, 0, st>>>(segs, prm); break;
+    case 5: select_kernel<LPR, VEC, 5><<<grid, 256, 0, st>>>(segs, prm); break;
+    case 6: select_kernel<LPR, VEC, 6><<<grid, 256, 0, st>>>(segs, prm); break;
+    case 7: select_kernel<LPR, VEC, 7><<<grid, 256, 0, st>>>(segs, prm); break;
+    default: select_kernel<LPR, VEC, 8><<<grid, 256, 0, st>>>(segs, prm); break;
+  }
+}
+
+template <int VEC>
+static void launch_select_lpr(int lpr, int upl, unsigned grid, cudaStream_t st, const Segs& segs,
+                              const SelectParams& prm) {
+  switch (lpr) {
+    case 1: launch_select<1, VEC>(upl, grid, st, segs, prm); break;
+    case 2: launch_select<2, VEC>(upl, grid, st, segs, prm); break;
+    case 4: launch_select<4, VEC>(upl, grid, st, segs, prm); break;
+    case 8: launch_select<8, VEC>(upl, grid, st, segs, prm); break;
+    case 16: launch_select<16, VEC>(upl, grid, st, segs, prm); break;
+    default: launch_select<32, VEC>(upl, grid, st, segs, prm); break;
+  }
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" int rn_boxmap_op(const rn_pyramid_t* pyr, int batch, int op, const rn_maps_t* in, const rn_maps_t* out,
+                            void* stream) {
+  RN_REQUIRE(pyr && maps_present(in) && maps_present(out), RN_ERR_BAD_ARG, "rn_boxmap_op: NULL input");
+  RN_REQUIRE(batch >= 0, RN_ERR_BAD_ARG, "rn_boxmap_op: negative batch");
+  RN_REQUIRE(op >= RN_BOXOP_DECODE && op <= RN_BOXOP_CORNER_TO_CENTRE, RN_ERR_BAD_ARG, "rn_boxmap_op: unknown op %d", op);
+  for (int l = 0; l < pyr->num_levels; ++l)
+    RN_REQUIRE(in->p[l] && out->p[l] && ((((uintptr_t)in->p[l]) | ((uintptr_t)out->p[l])) & 15) == 0, RN_ERR_BAD_ARG,
+               "rn_boxmap_op: level %d map missing or not 16-byte aligned", l);
+  const long long total = pyr->anchors_per_image * (long long)batch;
+  if (total == 0) return RN_OK;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  boxmap_op_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*pyr, batch, op, make_ptrs(in), make_ptrs(out));
+  RN_CUDA_CHECK_LAUNCH("rn_boxmap_op");
+  return RN_OK;
+}
+
+extern "C" int rn_decode_boxes(const rn_pyramid_t* pyr, int batch, const rn_maps_t* deltas, const rn_maps_t* boxes,
+                               void* stream) {
+  return rn_boxmap_op(pyr, batch, RN_BOXOP_DECODE, deltas, boxes, stream);
+}
+
+extern "C" int rn_classmap_fg(int64_t rows, int num_classes, const float* d_classmap, float thr, uint8_t* d_fg_mask,
+                              void* stream) {
+  RN_REQUIRE(rows >= 0 && num_classes >= 1, RN_ERR_BAD_ARG, "rn_classmap_fg: bad shape");
+  if (rows == 0) return RN_OK;
+  RN_REQUIRE(d_classmap && d_fg_mask, RN_ERR_BAD_ARG, "rn_classmap_fg: NULL pointer");
+  long long blocks = (rows + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  classmap_fg_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, num_classes, d_classmap, thr, d_fg_mask);
+  RN_CUDA_CHECK_LAUNCH("rn_classmap_fg");
+  return RN_OK;
+}
+
+extern "C" size_t rn_select_workspace_bytes(int batch, int capacity) {
+  if (batch < 0 || capacity < 0) return 0;
+  const size_t n = (size_t)batch * (size_t)capacity;
+  size_t bytes = 3 * align256(n * 4);
+  if (needs_global_sort(capacity)) bytes += align256((size_t)batch * host_next_pow2((unsigned)capacity) * 12);
+  return bytes + 256;
+}
+
+extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* scores,
+                                int scores_are_logits, const rn_maps_t* regs, int regs_are_deltas, float score_thr,
+                                int topk_per_level, int capacity, float* d_cand_boxes, float* d_cand_scores,
+                                int32_t* d_cand_classes, int32_t* d_cand_anchor, int32_t* d_cand_count,
+                                uint32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream) {
+  RN_REQUIRE(pyr && maps_present(scores) && maps_present(regs), RN_ERR_BAD_ARG, "rn_decode_select: NULL input");
+  RN_REQUIRE(d_cand_boxes && d_cand_scores && d_cand_classes && d_cand_anchor && d_cand_count && d_workspace,
+             RN_ERR_BAD_ARG, "rn_decode_select: NULL output");
+  RN_REQUIRE(batch >= 0 && num_classes >= 1 && capacity >= 1, RN_ERR_BAD_ARG, "rn_decode_select: bad sizes");
+  RN_REQUIRE(workspace_bytes >= rn_select_workspace_bytes(batch, capacity), RN_ERR_CAPACITY,
+             "rn_decode_select: workspace too small");
+  RN_REQUIRE(((uintptr_t)d_cand_boxes & 15) == 0, RN_ERR_BAD_ARG, "d_cand_boxes must be 16-byte aligned");
+  if (batch == 0) return RN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  rn_rows_t rows;
+  rn_rows_from_pyramid(pyr, batch, &rows);
+  const Segs segs = make_segs(&rows);
+  bool vec4 = num_classes % 4 == 0;
+  for (int l = 0; l < pyr->num_levels; ++l) {
+    RN_REQUIRE(scores->p[l] && regs->p[l], RN_ERR_BAD_ARG, "rn_decode_select: missing map for level %d", l);
+    RN_REQUIRE(((uintptr_t)regs->p[l] & 15) == 0, RN_ERR_BAD_ARG, "regs maps must be 16-byte aligned");
+    if ((uintptr_t)scores->p[l] & 15) vec4 = false;
+  }
+  const size_t n = (size_t)batch * capacity;
+  char* ws = (char*)d_workspace;
+  SelectParams sp;
+  sp.scores = make_ptrs(scores);
+  sp.num_classes = num_classes;
+  sp.units_per_row = vec4 ? num_classes / 4 : num_classes;
+  sp.images = batch;
+  sp.capacity = capacity;
+  sp.thr = score_thr;
+  sp.is_logits = scores_are_logits;
+  sp.ws_anchor = (int32_t*)ws; ws += align256(n * 4);
+  sp.ws_score = (float*)ws; ws += align256(n * 4);
+  sp.ws_class = (int32_t*)ws; ws += align256(n * 4);
+  sp.count = d_cand_count;
+  sp.status = d_status;
+  int lpr = 1;
+  while (lpr < 32 && (sp.units_per_row + lpr - 1) / lpr > 8) lpr <<= 1;
+  const int upl = (sp.units_per_row + lpr - 1) / lpr;
+  RN_REQUIRE(upl <= 8, RN_ERR_UNSUPPORTED, "rn_decode_select: more than %d classes", vec4 ? 1024 : 256);
+  cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * batch, st);
+  const long long total_rows = segs.start[RN_MAX_LEVELS];
+  long long blocks = (total_rows * lpr + 255) / 256;
+  const long long capb = (long long)num_sms() * 8;
+  if (blocks > capb) blocks = capb;
+  if (blocks < 1) blocks = 1;
+  if (vec4) launch_select_lpr<4>(lpr, upl, (unsigned)blocks, st, segs, sp);
+  else launch_select_lpr<1>(lpr, upl, (unsigned)blocks, st, segs, sp);
+  RN_CUDA_CHECK_LAUNCH("rn_decode_select(select)");
+
+  FinalizeParams fp;
+  fp.regs = make_ptrs(regs);
+  fp.regs_are_deltas = regs_are_deltas;
+  fp.capacity = capacity;
+  fp.topk = topk_per_level;
+  fp.ws_anchor = sp.ws_anchor;
+  fp.ws_score = sp.ws_score;
+  fp.ws_class = sp.ws_class;
+  fp.pad = host_next_pow2((unsigned)capacity);
+  fp.g_key = nullptr;
+  fp.g_pos = nullptr;
+  if (needs_global_sort(capacity)) {
+    fp.g_key = (unsigned long long*)ws;
+    fp.g_pos = (unsigned*)(ws + (size_t)batch * fp.pad * 8);
+  }
+  fp.out_boxes = (float4*)d_cand_boxes;
+  fp.out_scores = d_cand_scores;
+  fp.out_classes = d_cand_classes;
+  fp.out_anchor = d_cand_anchor;
+  fp.count = d_cand_count;
+  const size_t smem = sort_smem_bytes(capacity);
+  cudaFuncSetAttribute(cand_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
+  cand_finalize_kernel<<<batch, kSortThreads, smem, st>>>(*pyr, batch, fp);
+  RN_CUDA_CHECK_LAUNCH("rn_decode_select(finalize)");
+  return RN_OK;
+}
+
+extern "C" size_t rn_nms_workspace_bytes(int batch, int num_classes, int capacity) {
+  if (batch < 0 || capacity < 0 || num_classes < 0) return 0;
+  const size_t n = (size_t)batch * (size_t)capacity;
+  size_t bytes = 2 * align256(n * 4) + align256((size_t)batch * (num_classes + 1) * 4) +
+                 align256((size_t)batch * num_classes * 4);
+  if (needs_global_sort(capacity)) bytes += align256((size_t)batch * host_next_pow2((unsigned)capacity) * 12);
+  return bytes + 256;
+}
+
+extern "C" int rn_nms_classwise(int batch, int num_classes, int capacity, const float* d_cand_boxes,
+                                const float* d_cand_scores, const int32_t* d_cand_classes,
+                                const int32_t* d_cand_count, float iou_thr, int max_output_per_class,
+                                int out_capacity, float* d_det_boxes, float* d_det_scores, int32_t* d_det_classes,
+                                int32_t* d_det_index, int32_t* d_det_count, uint32_t* d_status, void* d_workspace,
+                                size_t workspace_bytes, void* stream) {
+  RN_REQUIRE(d_cand_boxes && d_cand_scores && d_cand_classes && d_cand_count, RN_ERR_BAD_ARG,
+             "rn_nms_classwise: NULL input");
+  RN_REQUIRE(d_det_boxes && d_det_scores && d_det_classes && d_det_index && d_det_count && d_workspace,
+             RN_ERR_BAD_ARG, "rn_nms_classwise: NULL output");
+  RN_REQUIRE(batch >= 0 && num_classes >= 1 && capacity >= 1 && out_capacity >= 1 && max_output_per_class >= 0,
+             RN_ERR_BAD_ARG, "rn_nms_classwise: bad sizes");
+  RN_REQUIRE(iou_thr >= 0.f && iou_thr <= 1.f, RN_ERR_BAD_ARG, "iou_threshold must be in [0, 1]");
+  RN_REQUIRE(workspace_bytes >= rn_nms_workspace_bytes(batch, num_classes, capacity), RN_ERR_CAPACITY,
+             "rn_nms_classwise: workspace too small");
+  RN_REQUIRE((((uintptr_t)d_cand_boxes | (uintptr_t)d_det_boxes) & 15) == 0, RN_ERR_BAD_ARG,
+             "box arrays must be 16-byte aligned");
+  if (batch == 0) return RN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)batch * capacity;
+  char* ws = (char*)d_workspace;
+  NmsParams p;
+  p.batch = batch;
+  p.num_classes = num_classes;
+  p.capacity = capacity;
+  p.out_capacity = out_capacity;
+  p.max_out = max_output_per_class;
+  p.iou_thr = iou_thr;
+  p.boxes = (const float4*)d_cand_boxes;
+  p.scores = d_cand_scores;
+  p.classes = d_cand_classes;
+  p.count = d_cand_count;
+  p.perm = (unsigned*)ws; ws += align256(n * 4);
+  p.kept = (unsigned*)ws; ws += align256(n * 4);
+  p.seg = (int32_t*)ws; ws += align256((size_t)batch * (num_classes + 1) * 4);
+  p.kept_count = (int32_t*)ws; ws += align256((size_t)batch * num_classes * 4);
+  p.pad = host_next_pow2((unsigned)capacity);
+  p.g_key = nullptr;
+  p.g_pos = nullptr;
+  if (needs_global_sort(capacity)) {
+    p.g_key = (unsigned long long*)ws;
+    p.g_pos = (unsigned*)(ws + (size_t)batch * p.pad * 8);
+  }
+  p.det_boxes = (float4*)d_det_boxes;
+  p.det_scores = d_det_scores;
+  p.det_classes = d_det_classes;
+  p.det_index = d_det_index;
+  p.det_count = d_det_count;
+  p.status = d_status;
+  p.kept_cap = max_output_per_class < capacity ? max_output_per_class : capacity;
+  if (p.kept_cap < 1) p.kept_cap = 1;
+  const size_t greedy_smem = (size_t)kNmsWarps * p.kept_cap * sizeof(NmsBox);
+  RN_REQUIRE(greedy_smem <= 200 * 1024, RN_ERR_UNSUPPORTED,
+             "rn_nms_classwise: max_output_per_class too large for shared memory (limit %d)",
+             (int)(200 * 1024 / (kNmsWarps * sizeof(NmsBox))));
+  cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
+  cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  nms_sort_kernel<<<batch, kSortThreads, sort_smem_bytes(capacity), st>>>(p);
+  RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(sort)");
+  const long long pairs = (long long)batch * num_classes;
+  nms_greedy_kernel<<<(unsigned)((pairs + kNmsWarps - 1) / kNmsWarps), kNmsWarps * 32, greedy_smem, st>>>(p);
+  RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(greedy)");
+  nms_compact_kernel<<<batch, 256, 0, st>>>(p);
+  RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(compact)");
+  return RN_OK;
+}

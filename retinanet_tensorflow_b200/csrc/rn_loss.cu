@@ -1,0 +1,681 @@
+// K2/K3: fused classification loss (focal | BCE | balanced BCE, +dice) and Huber regression loss,
+// forward and backward in one pass over the logits (losses.py:6-15,50-60,96-110,115-152;
+// utils.process_labels_and_logits' sigmoid and trainable masking, utils.py:249,270).
+//
+// The kernels stream `[rows, C]` logits once (128-bit loads), take the per-row compact label
+// (class | background | ignored) written by K1, and write d(loss)/d(logits) with the global
+// normalisers already applied.  Normalisers (M, num_fg, per-class sums) live in a small
+// double-precision stats vector in device memory so that nothing is synchronised with the host
+// and the multi-GPU exchange is one all-reduce of that vector.  Loss sums are reduced
+// warp -> block -> (per-block partials, fixed-order final pass by the last block), so results
+// are run-to-run deterministic.
+#include "rn_common.cuh"
+
+namespace rn {
+
+constexpr int kLossThreads = 256;
+constexpr int kMaxLossBlocks = 2048;
+
+struct LossScalars {
+  float focus, alpha, one_minus_alpha, eps;
+};
+
+// ---- per-element math --------------------------------------------------------------------------
+// Focal (losses.py:9-13): loss = -alpha_t * (1 - p_t)^focus * log(p_t + eps), with the naive
+// 1 - p and eps inside the log; gradient follows the autodiff chain through the same
+// float32 intermediates.
+template <bool GRAD>
+__device__ __forceinline__ void focal_elem(float x, bool z, const LossScalars& sc, float& loss, float& grad) {
+  const float p = sigmoid_f32(x);
+  const float q = fsub(1.0f, p);
+  const float pt = z ? p : q;
+  const float at = z ? sc.alpha : sc.one_minus_alpha;
+  const float w = fsub(1.0f, pt);
+  const float pe = fadd(pt, sc.eps);
+  const float lg = logf(pe);
+  float mod, dmod;  // w^focus and focus * w^(focus-1)
+  if (sc.focus == 2.0f) {
+    mod = w * w;
+    dmod = 2.0f * w;
+  } else {
+    mod = powf(w, sc.focus);
+    dmod = sc.focus * powf(w, sc.focus - 1.0f);
+  }
+  loss = (-at * mod) * lg;
+  if (GRAD) {
+    const float d_pt = -at * (mod / pe - dmod * lg);
+    grad = (z ? d_pt : -d_pt) * (p * q);
+  }
+}
+
+// tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log1p(exp(-|x|)); d/dx = p - z.
+template <bool GRAD>
+__device__ __forceinline__ void bce_elem(float x, float z, float& loss, float& p_out) {
+  const float e = expf(-fabsf(x));
+  loss = fadd(fsub(fmaxf(x, 0.0f), fmul(x, z)), log1pf(e));
+  if (GRAD) {
+    const float r = fdiv(1.0f, fadd(1.0f, e));
+    p_out = x >= 0.0f ? r : e * r;
+  }
+}
+
+struct ClsParams {
+  Ptrs logits, label, dlogits;
+  LossScalars sc;
+  const double* stats;
+  double* stats_out;     // stats (written: RN_STAT_CLS_SUM)
+  double* partials;      // [gridDim.x]
+  unsigned* ticket;
+  int num_classes;
+  unsigned cv;           // units (of VEC elements) per row
+  int write_grad;
+};
+
+// MODE: RN_CLS_NONE/FOCAL/BCE/BALANCED_BCE;  DICE: add dice gradient;  DENSE: float labels
+// [rows, C] instead of compact int32;  VEC: elements per thread-unit (4 -> 128-bit accesses).
+template <int MODE, bool DICE, bool DENSE, int VEC>
+__global__ void __launch_bounds__(kLossThreads)
+cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsParams prm) {
+  extern __shared__ float s_tab[];  // [4][C]: w_pos, w_neg, dice A, dice B
+  __shared__ double s_red[32];
+  const int C = prm.num_classes;
+  float* s_wpos = s_tab;
+  float* s_wneg = s_tab + C;
+  float* s_da = s_tab + 2 * C;
+  float* s_db = s_tab + 3 * C;
+
+  const double M = prm.stats[RN_STAT_TRAINABLE];
+  const double nfg = prm.stats[RN_STAT_NUM_FG];
+  const float inv_fg = (float)(1.0 / fmax(nfg, 1.0));                  // losses.py:121
+  const float inv_mc = M > 0 ? (float)(1.0 / (M * (double)C)) : 0.0f;  // reduce_mean over [M, C]
+  if (MODE == RN_CLS_BALANCED_BCE || DICE) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double npos = prm.stats[RN_STAT_NPOS(c)];
+      if (MODE == RN_CLS_BALANCED_BCE) {  // losses.py:99-103, axis=0
+        s_wpos[c] = (float)((M - npos) / M);
+        s_wneg[c] = (float)(npos / M);
+      }
+      if (DICE) {  // d/dp [1 - 2I/U] / C = (z * A + B),  A = -2/(C U), B = 2 I/(C U^2)
+        const double I = prm.stats[RN_STAT_INTER(C, c)];
+        const double U = npos + prm.stats[RN_STAT_PSUM(C, c)];
+        s_da[c] = (float)(-2.0 / ((double)C * U));
+        s_db[c] = (float)(2.0 * I / ((double)C * U * U));
+      }
+    }
+    __syncthreads();
+  }
+
+  const long long total_units = segs.start[RN_MAX_LEVELS] * (long long)prm.cv;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < total_units; u += stride) {
+    const long long r = u / prm.cv;
+    const int c0 = (int)(u - r * prm.cv) * VEC;
+    const int s = seg_of(segs, r);
+    const long long rl = r - segs.start[s];
+    const long long off = rl * C + c0;
+    const float* xp = reinterpret_cast<const float*>(prm.logits.p[s]) + off;
+    float x[VEC], z[VEC], g[VEC];
+    bool trainable = true;
+    if constexpr (VEC == 4) {
+      const float4 v = ld_stream4(xp);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+      x[0] = __ldcs(xp);
+    }
+    if (DENSE) {
+      const float* zp = reinterpret_cast<const float*>(prm.label.p[s]) + off;
+      if constexpr (VEC == 4) {
+        const float4 v = ld_stream4(zp);
+        z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+      } else {
+        z[0] = __ldcs(zp);
+      }
+    } else {
+      const int lab = __ldg(reinterpret_cast<const int32_t*>(prm.label.p[s]) + rl);
+      trainable = lab != RN_LABEL_IGNORE;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) z[k] = (lab == c0 + k) ? 1.0f : 0.0f;
+    }
+    float lsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      g[k] = 0.0f;
+      if (!trainable) continue;
+      float p = 0.0f, loss = 0.0f;
+      bool have_p = false;
+      if (MODE == RN_CLS_FOCAL) {
+        float gr = 0.0f;
+        focal_elem<true>(x[k], z[k] == 1.0f, prm.sc, loss, gr);
+        g[k] = gr * inv_fg;
+      } else if (MODE == RN_CLS_BCE || MODE == RN_CLS_BALANCED_BCE) {
+        bce_elem<true>(x[k], z[k], loss, p);
+        have_p = true;
+        float wgt = inv_mc;
+        if (MODE == RN_CLS_BALANCED_BCE) {
+          const float wc = (z[k] == 1.0f) ? s_wpos[c0 + k] : s_wneg[c0 + k];
+          loss *= wc;
+          wgt *= wc;
+        }
+        g[k] = (p - z[k]) * wgt;
+      }
+      if (DICE) {
+        if (!have_p) p = sigmoid_f32(x[k]);
+        g[k] += (z[k] * s_da[c0 + k] + s_db[c0 + k]) * (p * (1.0f - p));
+      }
+      lsum += loss;
+    }
+    acc += (double)lsum;
+    if (prm.write_grad) {
+      float* gp = reinterpret_cast<float*>(prm.dlogits.p[s]) + off;
+      if constexpr (VEC == 4) {
+        st_stream4(gp, make_float4(g[0], g[1], g[2], g[3]));
+      } else {
+        __stcs(gp, g[0]);
+      }
+    }
+  }
+
+  // ---- deterministic reduction of the loss sum
+  acc = block_sum(acc, s_red);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    prm.partials[blockIdx.x] = acc;
+    __threadfence();
+    const unsigned t = atomicAdd(prm.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(prm.partials + i);
+    v = block_sum(v, s_red);
+    if (threadIdx.x == 0) {
+      prm.stats_out[RN_STAT_CLS_SUM] = v;
+      *prm.ticket = 0;
+    }
+  }
+}
+
+// ---- per-class sums for dice: I_c = sum z p, P_c = sum p (losses.py:53-56) ---------------------
+struct SumsParams {
+  Ptrs logits, label;
+  double* stats_out;
+  double* partials;  // [gridDim.x][2C]
+  unsigned* ticket;
+  int num_classes;
+  int cv;   // units per row
+  int ry;   // rows per block iteration
+};
+
+template <bool DENSE, int VEC>
+__global__ void __launch_bounds__(1024) cls_sums_kernel(const __grid_constant__ Segs segs,
+                                                        const __grid_constant__ SumsParams prm) {
+  extern __shared__ double s_acc[];  // [ry][2C]
+  const int C = prm.num_classes;
+  const int tx = threadIdx.x % prm.cv, ty = threadIdx.x / prm.cv;
+  const long long total_rows = segs.start[RN_MAX_LEVELS];
+  double ai[VEC], ap[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) ai[k] = ap[k] = 0.0;
+  const int c0 = tx * VEC;
+  if (ty < prm.ry) {
+    for (long long r = (long long)blockIdx.x * prm.ry + ty; r < total_rows; r += (long long)gridDim.x * prm.ry) {
+      const int s = seg_of(segs, r);
+      const long long rl = r - segs.start[s];
+      const long long off = rl * C + c0;
+      const float* xp = reinterpret_cast<const float*>(prm.logits.p[s]) + off;
+      float x[VEC], z[VEC];
+      if constexpr (VEC == 4) {
+        const float4 v = ld_stream4(xp);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+      } else {
+        x[0] = __ldcs(xp);
+      }
+      if (DENSE) {
+        const float* zp = reinterpret_cast<const float*>(prm.label.p[s]) + off;
+        if constexpr (VEC == 4) {
+          const float4 v = ld_stream4(zp);
+          z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w;
+        } else {
+          z[0] = __ldcs(zp);
+        }
+      } else {
+        const int lab = __ldg(reinterpret_cast<const int32_t*>(prm.label.p[s]) + rl);
+        if (lab == RN_LABEL_IGNORE) continue;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) z[k] = (lab == c0 + k) ? 1.0f : 0.0f;
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float p = sigmoid_f32(x[k]);
+        ai[k] += (double)(z[k] * p);
+        ap[k] += (double)p;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      s_acc[(size_t)ty * 2 * C + c0 + k] = ai[k];
+      s_acc[(size_t)ty * 2 * C + C + c0 + k] = ap[k];
+    }
+  }
+  __syncthreads();
+  double* mine = prm.partials + (size_t)blockIdx.x * 2 * C;
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    double v = 0.0;
+    for (int y = 0; y < prm.ry; ++y) v += s_acc[(size_t)y * 2 * C + j];
+    mine[j] = v;
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(prm.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+      double v = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(prm.partials + (size_t)b * 2 * C + j);
+      prm.stats_out[RN_STATS_HEADER + C + j] = v;  // INTER block then PSUM block
+    }
+    if (threadIdx.x == 0) *prm.ticket = 0;
+  }
+}
+
+// ---- dense-label statistics (compat API): M = rows, num_fg = #rows with max z > 0.5, n_pos ------
+__global__ void dense_label_stats_kernel(long long rows, int C, const float* __restrict__ labels, double* stats) {
+  int n_fg = 0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      const float z = labels[r * C + c];
+      mx = fmaxf(mx, z);
+      if (z != 0.0f) atomicAdd(stats + RN_STAT_NPOS(c), (double)z);
+    }
+    n_fg += mx > 0.5f;  // utils.classmap_decode, utils.py:173-174
+  }
+  n_fg = warp_sum(n_fg);
+  if ((threadIdx.x & 31) == 0 && n_fg) atomicAdd(stats + RN_STAT_NUM_FG, (double)n_fg);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + RN_STAT_TRAINABLE, (double)rows);
+}
+
+// ---- Huber (tf.losses.huber_loss, delta = 1, SUM_BY_NONZERO_WEIGHTS; losses.py:144-152) ---------
+struct HuberParams {
+  Ptrs pred, target, label, fg_mask, dpred;
+  const double* stats;
+  double* stats_out;
+  double* partials;
+  unsigned* ticket;
+};
+
+__global__ void __launch_bounds__(kLossThreads)
+huber_kernel(const __grid_constant__ Segs segs, const __grid_constant__ HuberParams prm) {
+  __shared__ double s_red[32];
+  const long long total = segs.start[RN_MAX_LEVELS];
+  const double nfg = prm.stats[RN_STAT_NUM_FG];
+  const float gscale = nfg > 0 ? (float)(1.0 / (4.0 * nfg)) : 0.0f;
+  double acc = 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total;
+       r += (long long)gridDim.x * blockDim.x) {
+    const int s = seg_of(segs, r);
+    const long long rl = r - segs.start[s];
+    bool fg;
+    if (prm.label.p[0]) {
+      fg = __ldg(reinterpret_cast<const int32_t*>(prm.label.p[s]) + rl) >= 0;
+    } else {
+      fg = reinterpret_cast<const unsigned char*>(prm.fg_mask.p[s])[rl] != 0;
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fg) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(prm.pred.p[s]) + rl);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(prm.target.p[s]) + rl);
+      const float e[4] = {fsub(p.x, t.x), fsub(p.y, t.y), fsub(p.z, t.z), fsub(p.w, t.w)};
+      float ls = 0.f, gg[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float ae = fabsf(e[k]);
+        const float q = fminf(ae, 1.0f);
+        ls += fadd(0.5f * fmul(q, q), fsub(ae, q));  // 0.5 q^2 + delta (|e| - q)
+        gg[k] = fminf(fmaxf(e[k], -1.0f), 1.0f) * gscale;
+      }
+      acc += (double)ls;
+      g = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    }
+    if (prm.dpred.p[0]) __stcs(reinterpret_cast<float4*>(prm.dpred.p[s]) + rl, g);
+  }
+  acc = block_sum(acc, s_red);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    prm.partials[blockIdx.x] = acc;
+    __threadfence();
+    const unsigned t = atomicAdd(prm.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(prm.partials + i);
+    v = block_sum(v, s_red);
+    if (threadIdx.x == 0) {
+      prm.stats_out[RN_STAT_HUBER_SUM] = v;
+      *prm.ticket = 0;
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(int C, int mode, const double* __restrict__ stats, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double M = stats[RN_STAT_TRAINABLE], nfg = stats[RN_STAT_NUM_FG];
+  const int base = mode & 15;
+  double cls = 0.0;
+  if (base == RN_CLS_FOCAL) cls += stats[RN_STAT_CLS_SUM] / fmax(nfg, 1.0);
+  if (base == RN_CLS_BCE || base == RN_CLS_BALANCED_BCE) cls += M > 0 ? stats[RN_STAT_CLS_SUM] / (M * (double)C) : 0.0;
+  if (mode & RN_CLS_DICE_FLAG) {
+    double d = 0.0;
+    for (int c = 0; c < C; ++c) {
+      const double I = stats[RN_STAT_INTER(C, c)];
+      const double U = stats[RN_STAT_NPOS(c)] + stats[RN_STAT_PSUM(C, c)];
+      d += 1.0 - 2.0 * I / U;
+    }
+    cls += d / (double)C;
+  }
+  out[0] = (float)cls;
+  out[1] = nfg > 0 ? (float)(stats[RN_STAT_HUBER_SUM] / (4.0 * nfg)) : 0.0f;
+  out[2] = (float)nfg;
+  out[3] = (float)M;
+}
+
+// ---- elementwise, unreduced (the reference functions' own return shape) -------------------------
+__global__ void cls_elementwise_kernel(long long n, int C, const float* __restrict__ labels,
+                                       const float* __restrict__ logits, int mode, LossScalars sc,
+                                       const float* __restrict__ w_pos, const float* __restrict__ w_neg,
+                                       float* __restrict__ loss_out, float* __restrict__ grad_out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = logits[i], z = labels[i];
+    float loss = 0.f, grad = 0.f;
+    if (mode == RN_CLS_FOCAL) {
+      focal_elem<true>(x, z == 1.0f, sc, loss, grad);
+    } else {
+      float p;
+      bce_elem<true>(x, z, loss, p);
+      grad = p - z;
+      if (mode == RN_CLS_BALANCED_BCE && w_pos) {
+        const int c = (int)(i % C);
+        const float w = (z == 1.0f) ? w_pos[c] : w_neg[c];
+        loss *= w;
+        grad *= w;
+      }
+    }
+    if (loss_out) loss_out[i] = loss;
+    if (grad_out) grad_out[i] = grad;
+  }
+}
+
+// Backward of any loss of the per-class sums I_c = sum z p, P_c = sum p (dice / jaccard /
+// fixed-IoU, losses.py:37-73):  d/dx[m,c] = (z * a[c] + b[c]) * p (1 - p).
+__global__ void colsum_backward_kernel(long long n, int C, const float* __restrict__ labels,
+                                       const float* __restrict__ logits, const float* __restrict__ a,
+                                       const float* __restrict__ b, float* __restrict__ grad) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float p = sigmoid_f32(logits[i]);
+    grad[i] = (labels[i] * a[c] + b[c]) * (p * (1.0f - p));
+  }
+}
+
+__global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = sigmoid_f32(in[i]);
+}
+
+static unsigned loss_grid(long long units, int threads, int per_sm) {
+  long long blocks = (units + threads - 1) / threads;
+  long long cap = (long long)num_sms() * per_sm;
+  if (cap > kMaxLossBlocks) cap = kMaxLossBlocks;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+static bool aligned16(const rn_maps_t* m, int n) {
+  for (int i = 0; i < n; ++i)
+    if (((uintptr_t)m->p[i]) & 15) return false;
+  return true;
+}
+
+template <int MODE, bool DICE, bool DENSE>
+static void launch_cls(bool vec4, unsigned grid, size_t smem, cudaStream_t st, const Segs& segs, const ClsParams& prm) {
+  if (vec4)
+    cls_loss_kernel<MODE, DICE, DENSE, 4><<<grid, kLossThreads, smem, st>>>(segs, prm);
+  else
+    cls_loss_kernel<MODE, DICE, DENSE, 1><<<grid, kLossThreads, smem, st>>>(segs, prm);
+}
+
+template <int MODE, bool DICE>
+static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaStream_t st, const Segs& segs,
+                        const ClsParams& prm) {
+  if (dense)
+    launch_cls<MODE, DICE, true>(vec4, grid, smem, st, segs, prm);
+  else
+    launch_cls<MODE, DICE, false>(vec4, grid, smem, st, segs, prm);
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" size_t rn_loss_workspace_bytes(int num_classes) {
+  const size_t per_block = (size_t)(2 * (num_classes > 0 ? num_classes : 1)) * sizeof(double);
+  return 256 + (size_t)kMaxLossBlocks * per_block;
+}
+
+static int check_rows(const rn_rows_t* rows, const char* who) {
+  RN_REQUIRE(rows, RN_ERR_BAD_ARG, "%s: NULL rows", who);
+  RN_REQUIRE(rows->num_segments >= 1 && rows->num_segments <= RN_MAX_LEVELS, RN_ERR_BAD_SHAPE,
+             "%s: num_segments must be in 1..%d", who, RN_MAX_LEVELS);
+  for (int i = 0; i < rows->num_segments; ++i) RN_REQUIRE(rows->rows[i] >= 0, RN_ERR_BAD_SHAPE, "%s: negative rows", who);
+  return RN_OK;
+}
+
+extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits, const rn_maps_t* label,
+                           int dense_labels, double* d_stats, void* d_workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_rows(rows, "rn_cls_sums");
+  if (rc) return rc;
+  RN_REQUIRE(maps_present(logits) && maps_present(label) && d_stats && d_workspace, RN_ERR_BAD_ARG,
+             "rn_cls_sums: NULL input");
+  RN_REQUIRE(num_classes >= 1, RN_ERR_BAD_ARG, "rn_cls_sums: num_classes must be >= 1");
+  RN_REQUIRE(workspace_bytes >= rn_loss_workspace_bytes(num_classes), RN_ERR_CAPACITY, "rn_cls_sums: workspace too small");
+  const Segs segs = make_segs(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec4 = (num_classes % 4 == 0) && aligned16(logits, rows->num_segments) &&
+                    (!dense_labels || aligned16(label, rows->num_segments));
+  const int vec = vec4 ? 4 : 1;
+  SumsParams prm;
+  prm.logits = make_ptrs(logits);
+  prm.label = make_ptrs(label);
+  prm.stats_out = d_stats;
+  prm.ticket = reinterpret_cast<unsigned*>(d_workspace);
+  prm.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
+  prm.num_classes = num_classes;
+  prm.cv = num_classes / vec;
+  RN_REQUIRE(prm.cv <= 1024, RN_ERR_UNSUPPORTED, "rn_cls_sums: too many classes");
+  prm.ry = 256 / prm.cv > 0 ? 256 / prm.cv : 1;
+  const int threads = prm.cv * prm.ry;
+  const size_t smem = (size_t)prm.ry * 2 * num_classes * sizeof(double);
+  RN_REQUIRE(smem <= 200 * 1024, RN_ERR_UNSUPPORTED, "rn_cls_sums: too many classes for shared memory");
+  const long long total_rows = segs.start[RN_MAX_LEVELS];
+  cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
+  unsigned grid = loss_grid((total_rows + prm.ry - 1) / prm.ry, 1, 4);
+#define RN_LAUNCH_SUMS(DENSE, VEC)                                                                             \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      cudaFuncSetAttribute(cls_sums_kernel<DENSE, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cls_sums_kernel<DENSE, VEC><<<grid, threads, smem, st>>>(segs, prm);                                       \
+  } while (0)
+  if (dense_labels) {
+    if (vec4) RN_LAUNCH_SUMS(true, 4); else RN_LAUNCH_SUMS(true, 1);
+  } else {
+    if (vec4) RN_LAUNCH_SUMS(false, 4); else RN_LAUNCH_SUMS(false, 1);
+  }
+#undef RN_LAUNCH_SUMS
+  RN_CUDA_CHECK_LAUNCH("rn_cls_sums");
+  return RN_OK;
+}
+
+extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
+                                   const rn_maps_t* label, int dense_labels, int mode, float focus, float alpha,
+                                   float eps, const rn_maps_t* dlogits, double* d_stats, void* d_workspace,
+                                   size_t workspace_bytes, void* stream) {
+  int rc = check_rows(rows, "rn_cls_loss_fwd_bwd");
+  if (rc) return rc;
+  RN_REQUIRE(maps_present(logits) && maps_present(label) && d_stats && d_workspace, RN_ERR_BAD_ARG,
+             "rn_cls_loss_fwd_bwd: NULL input");
+  RN_REQUIRE(num_classes >= 1, RN_ERR_BAD_ARG, "rn_cls_loss_fwd_bwd: num_classes must be >= 1");
+  RN_REQUIRE(workspace_bytes >= rn_loss_workspace_bytes(num_classes), RN_ERR_CAPACITY,
+             "rn_cls_loss_fwd_bwd: workspace too small");
+  const int base = mode & 15;
+  const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
+  RN_REQUIRE(base >= RN_CLS_NONE && base <= RN_CLS_BALANCED_BCE && (mode & ~(15 | RN_CLS_DICE_FLAG)) == 0,
+             RN_ERR_BAD_ARG, "rn_cls_loss_fwd_bwd: unknown mode %d", mode);
+  RN_REQUIRE(base != RN_CLS_NONE || dice, RN_ERR_BAD_ARG, "rn_cls_loss_fwd_bwd: empty mode");
+  const Segs segs = make_segs(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool grad = maps_present(dlogits);
+  const bool vec4 = (num_classes % 4 == 0) && aligned16(logits, rows->num_segments) &&
+                    (!grad || aligned16(dlogits, rows->num_segments)) &&
+                    (!dense_labels || aligned16(label, rows->num_segments));
+  ClsParams prm;
+  prm.logits = make_ptrs(logits);
+  prm.label = make_ptrs(label);
+  prm.dlogits = make_ptrs(grad ? dlogits : nullptr);
+  prm.sc.focus = focus;
+  prm.sc.alpha = alpha;
+  prm.sc.one_minus_alpha = 1.0f - alpha;
+  prm.sc.eps = eps;
+  prm.stats = d_stats;
+  prm.stats_out = d_stats;
+  prm.ticket = reinterpret_cast<unsigned*>(d_workspace);
+  prm.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
+  prm.num_classes = num_classes;
+  prm.cv = (unsigned)(num_classes / (vec4 ? 4 : 1));
+  prm.write_grad = grad ? 1 : 0;
+  const long long units = segs.start[RN_MAX_LEVELS] * (long long)prm.cv;
+  const unsigned grid = loss_grid(units, kLossThreads, 8);
+  const size_t smem = 4 * (size_t)num_classes * sizeof(float);
+  RN_REQUIRE(smem <= 48 * 1024, RN_ERR_UNSUPPORTED, "rn_cls_loss_fwd_bwd: too many classes");
+  cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
+  const bool dense = dense_labels != 0;
+  switch (base) {
+    case RN_CLS_FOCAL:
+      if (dice) launch_cls2<RN_CLS_FOCAL, true>(dense, vec4, grid, smem, st, segs, prm);
+      else launch_cls2<RN_CLS_FOCAL, false>(dense, vec4, grid, smem, st, segs, prm);
+      break;
+    case RN_CLS_BCE:
+      if (dice) launch_cls2<RN_CLS_BCE, true>(dense, vec4, grid, smem, st, segs, prm);
+      else launch_cls2<RN_CLS_BCE, false>(dense, vec4, grid, smem, st, segs, prm);
+      break;
+    case RN_CLS_BALANCED_BCE:
+      if (dice) launch_cls2<RN_CLS_BALANCED_BCE, true>(dense, vec4, grid, smem, st, segs, prm);
+      else launch_cls2<RN_CLS_BALANCED_BCE, false>(dense, vec4, grid, smem, st, segs, prm);
+      break;
+    default:
+      launch_cls2<RN_CLS_NONE, true>(dense, vec4, grid, smem, st, segs, prm);
+      break;
+  }
+  RN_CUDA_CHECK_LAUNCH("rn_cls_loss_fwd_bwd");
+  return RN_OK;
+}
+
+extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const rn_maps_t* target,
+                                const rn_maps_t* label, const rn_maps_t* fg_mask, const rn_maps_t* dpred,
+                                double* d_stats, void* d_workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_rows(rows, "rn_huber_fwd_bwd");
+  if (rc) return rc;
+  RN_REQUIRE(maps_present(pred) && maps_present(target) && d_stats && d_workspace, RN_ERR_BAD_ARG,
+             "rn_huber_fwd_bwd: NULL input");
+  RN_REQUIRE(maps_present(label) || maps_present(fg_mask), RN_ERR_BAD_ARG, "rn_huber_fwd_bwd: need label or fg_mask");
+  RN_REQUIRE(workspace_bytes >= rn_loss_workspace_bytes(1), RN_ERR_CAPACITY, "rn_huber_fwd_bwd: workspace too small");
+  RN_REQUIRE(aligned16(pred, rows->num_segments) && aligned16(target, rows->num_segments) &&
+                 (!maps_present(dpred) || aligned16(dpred, rows->num_segments)),
+             RN_ERR_BAD_ARG, "rn_huber_fwd_bwd: maps must be 16-byte aligned");
+  const Segs segs = make_segs(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  HuberParams prm;
+  prm.pred = make_ptrs(pred);
+  prm.target = make_ptrs(target);
+  prm.label = make_ptrs(maps_present(label) ? label : nullptr);
+  prm.fg_mask = make_ptrs(maps_present(fg_mask) ? fg_mask : nullptr);
+  prm.dpred = make_ptrs(maps_present(dpred) ? dpred : nullptr);
+  prm.stats = d_stats;
+  prm.stats_out = d_stats;
+  prm.ticket = reinterpret_cast<unsigned*>(d_workspace);
+  prm.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
+  cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
+  const unsigned grid = loss_grid(segs.start[RN_MAX_LEVELS], kLossThreads, 8);
+  huber_kernel<<<grid, kLossThreads, 0, st>>>(segs, prm);
+  RN_CUDA_CHECK_LAUNCH("rn_huber_fwd_bwd");
+  return RN_OK;
+}
+
+extern "C" int rn_loss_finalize(int num_classes, int mode, const double* d_stats, float* d_out, void* stream) {
+  RN_REQUIRE(d_stats && d_out && num_classes >= 1, RN_ERR_BAD_ARG, "rn_loss_finalize: bad argument");
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(num_classes, mode, d_stats, d_out);
+  RN_CUDA_CHECK_LAUNCH("rn_loss_finalize");
+  return RN_OK;
+}
+
+extern "C" int rn_label_stats_dense(int64_t rows, int num_classes, const float* d_labels, double* d_stats,
+                                    void* stream) {
+  RN_REQUIRE(rows >= 0 && num_classes >= 1 && d_stats, RN_ERR_BAD_ARG, "rn_label_stats_dense: bad argument");
+  if (rows == 0) return RN_OK;
+  RN_REQUIRE(d_labels, RN_ERR_BAD_ARG, "rn_label_stats_dense: NULL labels");
+  dense_label_stats_kernel<<<loss_grid(rows, 256, 8), 256, 0, (cudaStream_t)stream>>>(rows, num_classes, d_labels,
+                                                                                     d_stats);
+  RN_CUDA_CHECK_LAUNCH("rn_label_stats_dense");
+  return RN_OK;
+}
+
+extern "C" int rn_cls_loss_elementwise(int64_t rows, int num_classes, const float* d_labels, const float* d_logits,
+                                       int mode, float focus, float alpha, float eps, const float* d_w_pos,
+                                       const float* d_w_neg, float* d_loss, float* d_grad, void* stream) {
+  RN_REQUIRE(rows >= 0 && num_classes >= 1, RN_ERR_BAD_ARG, "rn_cls_loss_elementwise: bad shape");
+  RN_REQUIRE(mode == RN_CLS_FOCAL || mode == RN_CLS_BCE || mode == RN_CLS_BALANCED_BCE, RN_ERR_BAD_ARG,
+             "rn_cls_loss_elementwise: unknown mode %d", mode);
+  RN_REQUIRE((d_w_pos == nullptr) == (d_w_neg == nullptr), RN_ERR_BAD_ARG, "w_pos and w_neg go together");
+  const long long n = (long long)rows * num_classes;
+  if (n == 0) return RN_OK;
+  RN_REQUIRE(d_labels && d_logits && (d_loss || d_grad), RN_ERR_BAD_ARG, "rn_cls_loss_elementwise: NULL pointer");
+  LossScalars sc{focus, alpha, 1.0f - alpha, eps};
+  cls_elementwise_kernel<<<loss_grid(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(n, num_classes, d_labels, d_logits,
+                                                                                 mode, sc, d_w_pos, d_w_neg, d_loss,
+                                                                                 d_grad);
+  RN_CUDA_CHECK_LAUNCH("rn_cls_loss_elementwise");
+  return RN_OK;
+}
+
+extern "C" int rn_colsum_backward(int64_t rows, int num_classes, const float* d_labels, const float* d_logits,
+                                  const float* d_a, const float* d_b, float* d_grad, void* stream) {
+  RN_REQUIRE(rows >= 0 && num_classes >= 1, RN_ERR_BAD_ARG, "rn_colsum_backward: bad shape");
+  const long long n = (long long)rows * num_classes;
+  if (n == 0) return RN_OK;
+  RN_REQUIRE(d_labels && d_logits && d_a && d_b && d_grad, RN_ERR_BAD_ARG, "rn_colsum_backward: NULL pointer");
+  colsum_backward_kernel<<<loss_grid(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(n, num_classes, d_labels, d_logits,
+                                                                                 d_a, d_b, d_grad);
+  RN_CUDA_CHECK_LAUNCH("rn_colsum_backward");
+  return RN_OK;
+}
+
+extern "C" int rn_sigmoid(int64_t n, const float* d_in, float* d_out, void* stream) {
+  RN_REQUIRE(n >= 0, RN_ERR_BAD_ARG, "rn_sigmoid: negative n");
+  if (n == 0) return RN_OK;
+  RN_REQUIRE(d_in && d_out, RN_ERR_BAD_ARG, "rn_sigmoid: NULL pointer");
+  sigmoid_kernel<<<loss_grid(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(n, d_in, d_out);
+  RN_CUDA_CHECK_LAUNCH("rn_sigmoid");
+  return RN_OK;
+}

@@ -1,0 +1,246 @@
+"""Batched, fused dense-head path on one B200: assign+encode -> loss fwd+bwd -> decode/select/NMS.
+
+`DenseHeadPath` owns every buffer of the path (compact labels, statistics vector, gradient
+buffers, candidate / detection lists, workspaces) and issues the kernels of librndense.so on
+the current CUDA stream; nothing synchronises with the host.  It is the fast equivalent of the
+reference's three call sites: `dataset.build_labels` per image on tf.data threads
+(dataset.py:167), `utils.process_labels_and_logits` + `losses.loss` in the training graph
+(train.py:218-220) and `utils.boxes_decode` + `nms_classwise` (train.py:68-75).
+
+Per-anchor tensors use the merged level-major layout: the concatenation over levels P3..P7
+of the reference's per-level `[B, H, W, A, K]` tensors (utils.merge_outputs order,
+utils.py:151-153).  A list of per-level tensors is accepted wherever a merged tensor is.
+
+Multi-GPU: one process per GPU, the batch sharded by image.  The only exchange is an
+all-reduce(sum) of slices of the float64 statistics vector (normalisers before the gradient
+pass, loss sums after it) through `torch.distributed`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._pyramid import level_rows, level_shapes, pyramid_for, split_merged
+from .levels import build_levels
+
+CLS_MODES = {
+    'focal': _lib.RN_CLS_FOCAL,
+    'bce': _lib.RN_CLS_BCE,
+    'balanced_bce': _lib.RN_CLS_BALANCED_BCE,
+    'bce_dice': _lib.RN_CLS_BCE | _lib.RN_CLS_DICE_FLAG,                    # the reference as committed
+    'balanced_bce_dice': _lib.RN_CLS_BALANCED_BCE | _lib.RN_CLS_DICE_FLAG,  # README.md:27
+    'focal_dice': _lib.RN_CLS_FOCAL | _lib.RN_CLS_DICE_FLAG,
+    'dice': _lib.RN_CLS_NONE | _lib.RN_CLS_DICE_FLAG,
+}
+
+_FLAG_MESSAGES = {
+    _lib.RN_FLAG_BOX_ORDER: 'assert_less_equal(box[:2], box[2:]) failed (utils.py:66-67)',
+    _lib.RN_FLAG_IOU_RANGE: 'IoU outside [0, 1] or NaN (utils.py:94)',
+    _lib.RN_FLAG_CAND_OVERFLOW: 'more candidates than `capacity`',
+    _lib.RN_FLAG_DET_OVERFLOW: 'more detections than `out_capacity`',
+    _lib.RN_FLAG_EMPTY_GT: 'an image has no ground-truth box (data_loaders/inferred.py:30)',
+}
+
+
+def raise_for_status(word, ignore=0):
+    """Turn the device status word into the exception the reference would raise."""
+    word = int(word) & ~ignore
+    if word & (_lib.RN_FLAG_BOX_ORDER | _lib.RN_FLAG_IOU_RANGE | _lib.RN_FLAG_EMPTY_GT):
+        raise AssertionError('; '.join(m for f, m in _FLAG_MESSAGES.items() if word & f))
+    if word:
+        raise ValueError('; '.join(m for f, m in _FLAG_MESSAGES.items() if word & f))
+
+
+class DenseHeadPath(object):
+    def __init__(self, image_size, num_classes, batch, max_gt, levels=None, *, cls_mode='focal',
+                 anchor_size_mode='tf1_int_trunc', neg_iou=0.4, pos_iou=0.5, focus=2.0, alpha=0.25, eps=1e-7,
+                 score_thr=0.5, nms_iou=0.5, max_output_per_class=1000, topk_per_level=0, capacity=4096,
+                 out_capacity=None, keep_iou=False, device=None, process_group=None):
+        self.device = _lib.require_cuda(device)
+        self.levels = build_levels() if levels is None else levels
+        self.names = list(self.levels)
+        self.image_size = (int(image_size[0]), int(image_size[1]))
+        self.num_classes = int(num_classes)
+        self.batch = int(batch)
+        self.max_gt = int(max_gt)
+        if cls_mode not in CLS_MODES:
+            raise ValueError('cls_mode must be one of %s' % sorted(CLS_MODES))
+        self.cls_mode = cls_mode
+        self.mode = CLS_MODES[cls_mode]
+        self.neg_iou, self.pos_iou = float(neg_iou), float(pos_iou)
+        self.focus, self.alpha, self.eps = float(focus), float(alpha), float(eps)
+        self.score_thr, self.nms_iou = float(score_thr), float(nms_iou)
+        self.max_output_per_class = int(max_output_per_class)
+        self.topk_per_level = int(topk_per_level or 0)
+        self.capacity = int(capacity)
+        self.out_capacity = int(out_capacity if out_capacity is not None else capacity)
+        self.group = process_group
+        self.pyr = pyramid_for(self.image_size, self.levels, anchor_size_mode, self.names)
+        self.anchors = int(self.pyr.anchors_per_image)
+        self.rows_total = self.batch * self.anchors
+        self.rows = _lib.Rows()
+        _lib.call('rn_rows_from_pyramid', C.byref(self.pyr), self.batch, C.byref(self.rows))
+
+        dev, B, R, Cn = self.device, self.batch, self.rows_total, self.num_classes
+        i32, f32 = torch.int32, torch.float32
+        self.matched = torch.empty((R,), dtype=i32, device=dev)
+        self.label = torch.empty((R,), dtype=i32, device=dev)
+        self.deltas = torch.empty((R, 4), dtype=f32, device=dev)
+        self.iou_max = torch.empty((R,), dtype=f32, device=dev) if keep_iou else None
+        self.stats = torch.zeros((_lib.RN_STATS_HEADER + 3 * Cn,), dtype=torch.float64, device=dev)
+        self.loss_out = torch.zeros((4,), dtype=f32, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self._loss_ws_bytes = _lib.lib.rn_loss_workspace_bytes(Cn)
+        self._loss_ws = torch.zeros((self._loss_ws_bytes,), dtype=torch.uint8, device=dev)
+        self._huber_ws = torch.zeros((_lib.lib.rn_loss_workspace_bytes(1),), dtype=torch.uint8, device=dev)
+        self.dlogits = None
+        self.dreg = None
+        cap, ocap = self.capacity, self.out_capacity
+        self.cand_boxes = torch.empty((B, cap, 4), dtype=f32, device=dev)
+        self.cand_scores = torch.empty((B, cap), dtype=f32, device=dev)
+        self.cand_classes = torch.empty((B, cap), dtype=i32, device=dev)
+        self.cand_anchor = torch.empty((B, cap), dtype=i32, device=dev)
+        self.cand_count = torch.zeros((B,), dtype=i32, device=dev)
+        self.det_boxes = torch.empty((B, ocap, 4), dtype=f32, device=dev)
+        self.det_scores = torch.empty((B, ocap), dtype=f32, device=dev)
+        self.det_classes = torch.empty((B, ocap), dtype=i32, device=dev)
+        self.det_index = torch.empty((B, ocap), dtype=i32, device=dev)
+        self.det_count = torch.zeros((B,), dtype=i32, device=dev)
+        self._sel_ws_bytes = _lib.lib.rn_select_workspace_bytes(B, cap)
+        self._sel_ws = torch.empty((self._sel_ws_bytes,), dtype=torch.uint8, device=dev)
+        self._nms_ws_bytes = _lib.lib.rn_nms_workspace_bytes(B, Cn, cap)
+        self._nms_ws = torch.empty((self._nms_ws_bytes,), dtype=torch.uint8, device=dev)
+
+        self._m_matched = self._merged_maps(self.matched, 4)
+        self._m_label = self._merged_maps(self.label, 4)
+        self._m_deltas = self._merged_maps(self.deltas, 16)
+        self._m_iou = self._merged_maps(self.iou_max, 4)
+
+    # ---- layout helpers ----------------------------------------------------------------------
+    def _merged_maps(self, tensor, bytes_per_anchor):
+        m = _lib.Maps()
+        if tensor is not None:
+            _lib.call('rn_maps_from_merged', C.byref(self.pyr), self.batch, _lib.ptr(tensor), bytes_per_anchor,
+                      C.byref(m))
+        return m
+
+    def _maps(self, x, trailing):
+        """rn_maps_t for a merged tensor [R, trailing] or a list/dict of per-level tensors."""
+        if isinstance(x, dict):
+            x = [x[n] for n in self.names]
+        if isinstance(x, (list, tuple)):
+            shapes = level_shapes(self.pyr)
+            if len(x) != len(shapes):
+                raise ValueError('expected %d levels' % len(shapes))
+            for t, (h, w, a) in zip(x, shapes):
+                if tuple(t.shape) != (self.batch, h, w, a, trailing) or t.dtype != torch.float32:
+                    raise ValueError('level tensor must be float32 [%d,%d,%d,%d,%d], got %s %s'
+                                     % (self.batch, h, w, a, trailing, tuple(t.shape), t.dtype))
+            ts = [t.contiguous() for t in x]
+            return _lib.maps_of(ts), ts
+        if tuple(x.shape) != (self.rows_total, trailing) or x.dtype != torch.float32:
+            raise ValueError('merged tensor must be float32 [%d,%d], got %s %s'
+                             % (self.rows_total, trailing, tuple(x.shape), x.dtype))
+        x = x.contiguous()
+        return self._merged_maps(x, 4 * trailing), x
+
+    def per_level(self, merged, trailing=()):
+        """Reference-shaped views `[B, H, W, A, ...]` keyed 'P3'.. of a merged buffer."""
+        return dict(zip(self.names, split_merged(self.pyr, self.batch, merged, trailing)))
+
+    def _allreduce(self, t):
+        """Sum `t` over the ranks (process_group=False disables; None = default group)."""
+        if self.group is False:
+            return
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, group=self.group)
+
+    # ---- stage 1: assignment + encoding (dataset.build_labels) ------------------------------
+    def assign(self, gt_boxes, gt_classes, gt_counts):
+        """gt_boxes f32 [B, max_gt, 4], gt_classes i32 [B, max_gt], gt_counts i32 [B] (device).
+        Fills self.matched / label / deltas and the label statistics."""
+        B = self.batch
+        if tuple(gt_boxes.shape) != (B, self.max_gt, 4) or gt_boxes.dtype != torch.float32:
+            raise ValueError('gt_boxes must be float32 [%d, %d, 4]' % (B, self.max_gt))
+        if tuple(gt_classes.shape) != (B, self.max_gt) or gt_classes.dtype != torch.int32:
+            raise ValueError('gt_classes must be int32 [%d, %d]' % (B, self.max_gt))
+        if tuple(gt_counts.shape) != (B,) or gt_counts.dtype != torch.int32:
+            raise ValueError('gt_counts must be int32 [%d]' % B)
+        self.stats.zero_()
+        _lib.call('rn_assign_encode', C.byref(self.pyr), B, _lib.ptr(gt_boxes.contiguous()),
+                  _lib.ptr(gt_classes.contiguous()), _lib.ptr(gt_counts.contiguous()), self.max_gt,
+                  self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched), C.byref(self._m_label),
+                  C.byref(self._m_deltas), C.byref(self._m_iou), _lib.ptr(self.stats), _lib.ptr(self.status),
+                  _lib.stream_ptr())
+        self._allreduce(self.stats)
+        return self.label, self.deltas
+
+    # ---- stage 2: loss forward + backward (utils.process_labels_and_logits + losses.loss) ---
+    def loss(self, logits, regression, want_grad=True):
+        """Returns self.loss_out (device f32 [4]: class loss, regression loss, num_fg, M); the
+        gradients w.r.t. the full logits / regression maps land in self.dlogits / self.dreg."""
+        m_logits, _ = self._maps(logits, self.num_classes)
+        m_reg, _ = self._maps(regression, 4)
+        st = _lib.stream_ptr()
+        Cn = self.num_classes
+        if want_grad:
+            if self.dlogits is None:
+                self.dlogits = torch.empty((self.rows_total, Cn), dtype=torch.float32, device=self.device)
+                self.dreg = torch.empty((self.rows_total, 4), dtype=torch.float32, device=self.device)
+            m_dlogits = self._merged_maps(self.dlogits, 4 * Cn)
+            m_dreg = self._merged_maps(self.dreg, 16)
+        else:
+            m_dlogits, m_dreg = _lib.Maps(), _lib.Maps()
+        if self.mode & _lib.RN_CLS_DICE_FLAG:
+            _lib.call('rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
+                      _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st)
+            self._allreduce(self.stats[_lib.RN_STATS_HEADER + Cn:])
+        _lib.call('rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
+                  self.mode, self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats),
+                  _lib.ptr(self._loss_ws), self._loss_ws_bytes, st)
+        _lib.call('rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas),
+                  C.byref(self._m_label), C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats),
+                  _lib.ptr(self._huber_ws), self._huber_ws.numel(), st)
+        self._allreduce(self.stats[_lib.RN_STAT_CLS_SUM:_lib.RN_STAT_HUBER_SUM + 1])
+        _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
+        return self.loss_out
+
+    # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
+    def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
+        m_scores, _ = self._maps(scores, self.num_classes)
+        m_reg, _ = self._maps(regression, 4)
+        _lib.call('rn_decode_select', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_scores),
+                  int(scores_are_logits), C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level,
+                  self.capacity, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
+                  _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self.status),
+                  _lib.ptr(self._sel_ws), self._sel_ws_bytes, _lib.stream_ptr())
+        return self.cand_count
+
+    def nms(self):
+        _lib.call('rn_nms_classwise', self.batch, self.num_classes, self.capacity, _lib.ptr(self.cand_boxes),
+                  _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes), _lib.ptr(self.cand_count), self.nms_iou,
+                  self.max_output_per_class, self.out_capacity, _lib.ptr(self.det_boxes), _lib.ptr(self.det_scores),
+                  _lib.ptr(self.det_classes), _lib.ptr(self.det_index), _lib.ptr(self.det_count),
+                  _lib.ptr(self.status), _lib.ptr(self._nms_ws), self._nms_ws_bytes, _lib.stream_ptr())
+        return self.det_count
+
+    def detect(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
+        self.select(scores, regression, scores_are_logits, regs_are_deltas)
+        self.nms()
+        return self.det_boxes, self.det_scores, self.det_classes, self.det_count
+
+    # ---- one whole step of the hot path -----------------------------------------------------
+    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression):
+        self.assign(gt_boxes, gt_classes, gt_counts)
+        self.loss(logits, regression)
+        self.detect(logits, regression)
+        return self.loss_out, self.det_count
+
+    def check_status(self, ignore=0):
+        """Synchronising: raises what the reference's runtime asserts would have raised."""
+        word = int(self.status.item())
+        self.status.zero_()
+        raise_for_status(word, ignore)

@@ -1,0 +1,227 @@
+"""K4/K5 parity (GPU): decode, candidate selection and class-wise NMS through the C ABI vs the
+oracle's utils.regression_postprocess / boxes_decode / merge_boxes_decoded / nms_classwise.
+Stage-wise on identical inputs: kept indices, classes and order are bit-exact; decoded boxes
+and sigmoid within 1e-5 relative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+import rn_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(name, batch, seed=11, **kw):
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS[name]
+    boxes, classes, counts = synthetic.gt_batch(wl, batch)
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, process_group=False, **kw)
+    path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
+    logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=seed, device='cuda')
+    return wl, path, logits, regs
+
+
+def _gpu_sigmoid(x):
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    out = torch.empty_like(x)
+    _lib.call('rn_sigmoid', x.numel(), _lib.ptr(x), _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def _gpu_decode(path, regs):
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    out = torch.empty_like(regs)
+    _lib.call('rn_decode_boxes', C.byref(path.pyr), path.batch, C.byref(path._merged_maps(regs, 16)),
+              C.byref(path._merged_maps(out, 16)), _lib.stream_ptr())
+    return out
+
+
+def _oracle_candidates(path, probs, boxes, b, topk=None):
+    """utils.boxes_decode per level for image b, merged P3..P7 (train.py:68-73); also the anchor
+    index of every candidate within the image."""
+    decoded, anchors, off = [], [], 0
+    p_lv = path.per_level(probs, (path.num_classes,))
+    b_lv = path.per_level(boxes, (4,))
+    for pn in path.names:
+        p = p_lv[pn][b].cpu().numpy()
+        d = oracle.boxes_decode(p, b_lv[pn][b].cpu().numpy())
+        fg = (p.max(-1) > np.float32(0.5)).reshape(-1)
+        idx = np.nonzero(fg)[0] + off
+        if topk is not None and topk < d.scores.shape[0]:
+            order = np.sort(np.argsort(-d.scores, kind='stable')[:topk])
+            d = oracle.BoxesDecoded(d.boxes[order], d.scores[order], d.class_ids[order])
+            idx = idx[order]
+        decoded.append(d)
+        anchors.append(idx)
+        off += fg.shape[0]
+    return oracle.merge_boxes_decoded(decoded), np.concatenate(anchors)
+
+
+def test_sigmoid_and_decode_boxes_match_oracle():
+    wl, path, logits, regs = _case('shapes', 2)
+    helpers.assert_close(_gpu_sigmoid(logits).cpu().numpy(), oracle.sigmoid(logits.cpu().numpy()), rtol=1e-6,
+                         what='sigmoid')
+    got = path.per_level(_gpu_decode(path, regs), (4,))
+    want_in = path.per_level(regs, (4,))
+    for pn in path.names:
+        sizes = oracle.anchor_size_normalised(path.levels[pn].anchor_sizes, np.array(path.image_size, np.int32))
+        want = oracle.regression_postprocess(want_in[pn].cpu().numpy(), sizes)
+        helpers.assert_close(got[pn].cpu().numpy(), want, rtol=1e-5, atol=1e-6, what='decode ' + pn)
+
+
+@pytest.mark.parametrize('name,batch', [('shapes', 3), ('voc', 2), ('coco', 2)])
+def test_select_and_nms_exact_on_identical_inputs(name, batch):
+    """Probabilities and decoded boxes are computed once (on the GPU) and handed to both sides:
+    every index, class, score, box and the output order must then be identical."""
+    import torch
+    wl, path, logits, regs = _case(name, batch, capacity=8192)
+    probs = _gpu_sigmoid(logits)
+    boxes = _gpu_decode(path, regs)
+    path.select(probs, boxes, scores_are_logits=False, regs_are_deltas=False)
+    path.nms()
+    torch.cuda.synchronize()
+    path.check_status()
+    total = 0
+    for b in range(batch):
+        cand, anchors = _oracle_candidates(path, probs, boxes, b)
+        n = int(path.cand_count[b])
+        assert n == cand.scores.shape[0]
+        np.testing.assert_array_equal(path.cand_anchor[b, :n].cpu().numpy(), anchors)
+        np.testing.assert_array_equal(path.cand_classes[b, :n].cpu().numpy(), cand.class_ids)
+        np.testing.assert_array_equal(path.cand_scores[b, :n].cpu().numpy(), cand.scores)
+        np.testing.assert_array_equal(path.cand_boxes[b, :n].cpu().numpy(), cand.boxes)
+        det, det_idx = oracle.nms_classwise(cand, wl.num_classes, return_indices=True)
+        m = int(path.det_count[b])
+        assert m == det.scores.shape[0]
+        np.testing.assert_array_equal(path.det_index[b, :m].cpu().numpy(), det_idx)
+        np.testing.assert_array_equal(path.det_classes[b, :m].cpu().numpy(), det.class_ids)
+        np.testing.assert_array_equal(path.det_scores[b, :m].cpu().numpy(), det.scores)
+        np.testing.assert_array_equal(path.det_boxes[b, :m].cpu().numpy(), det.boxes)
+        total += m
+    assert total > 0
+
+
+@pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2)])
+def test_fused_select_from_logits_and_deltas(name, batch):
+    """The fused path (sigmoid and decode inside the kernels) selects exactly what the
+    two-step path selects, and its values agree with the oracle's float32 math."""
+    import torch
+    wl, path, logits, regs = _case(name, batch, capacity=8192)
+    probs = _gpu_sigmoid(logits)
+    boxes = _gpu_decode(path, regs)
+    path.select(logits, regs)  # logits + deltas
+    torch.cuda.synchronize()
+    for b in range(batch):
+        cand, anchors = _oracle_candidates(path, probs, boxes, b)
+        n = int(path.cand_count[b])
+        assert n == anchors.shape[0]
+        np.testing.assert_array_equal(path.cand_anchor[b, :n].cpu().numpy(), anchors)
+        np.testing.assert_array_equal(path.cand_classes[b, :n].cpu().numpy(), cand.class_ids)
+        np.testing.assert_array_equal(path.cand_scores[b, :n].cpu().numpy(), cand.scores)
+        np.testing.assert_array_equal(path.cand_boxes[b, :n].cpu().numpy(), cand.boxes)
+        ref_scores = oracle.sigmoid(logits.cpu().numpy()).max(-1)
+        lv_rows = path.rows_total // path.batch
+        assert lv_rows == path.anchors and ref_scores.shape[0] == path.rows_total
+
+
+def test_topk_per_level_prefilter():
+    """Extension (not in the reference): k best per (image, level), identity for large k."""
+    import torch
+    wl, path, logits, regs = _case('voc', 2, capacity=8192, topk_per_level=25)
+    probs = _gpu_sigmoid(logits)
+    boxes = _gpu_decode(path, regs)
+    path.select(probs, boxes, scores_are_logits=False, regs_are_deltas=False)
+    torch.cuda.synchronize()
+    clipped = False
+    for b in range(2):
+        full, _ = _oracle_candidates(path, probs, boxes, b)
+        cand, anchors = _oracle_candidates(path, probs, boxes, b, topk=25)
+        clipped |= cand.scores.shape[0] < full.scores.shape[0]
+        n = int(path.cand_count[b])
+        assert n == anchors.shape[0]
+        np.testing.assert_array_equal(path.cand_anchor[b, :n].cpu().numpy(), anchors)
+        np.testing.assert_array_equal(path.cand_scores[b, :n].cpu().numpy(), cand.scores)
+    assert clipped
+
+
+def _nms_raw(boxes, scores, classes, num_classes, max_out=1000, iou_thr=0.5, capacity=None, out_capacity=None):
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    _lib.require_cuda()
+    n = boxes.shape[0]
+    cap = capacity or max(n, 1)
+    ocap = out_capacity or cap
+    cb = torch.zeros((1, cap, 4), device='cuda')
+    cs = torch.zeros((1, cap), device='cuda')
+    cc = torch.zeros((1, cap), dtype=torch.int32, device='cuda')
+    cb[0, :n] = torch.from_numpy(boxes).cuda()
+    cs[0, :n] = torch.from_numpy(scores).cuda()
+    cc[0, :n] = torch.from_numpy(classes.astype(np.int32)).cuda()
+    cnt = torch.tensor([n], dtype=torch.int32, device='cuda')
+    db = torch.zeros((1, ocap, 4), device='cuda')
+    ds = torch.zeros((1, ocap), device='cuda')
+    dc = torch.zeros((1, ocap), dtype=torch.int32, device='cuda')
+    di = torch.zeros((1, ocap), dtype=torch.int32, device='cuda')
+    dn = torch.zeros((1,), dtype=torch.int32, device='cuda')
+    status = torch.zeros((1,), dtype=torch.int32, device='cuda')
+    wsb = _lib.lib.rn_nms_workspace_bytes(1, num_classes, cap)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device='cuda')
+    _lib.call('rn_nms_classwise', 1, num_classes, cap, _lib.ptr(cb), _lib.ptr(cs), _lib.ptr(cc), _lib.ptr(cnt),
+              iou_thr, max_out, ocap, _lib.ptr(db), _lib.ptr(ds), _lib.ptr(dc), _lib.ptr(di), _lib.ptr(dn),
+              _lib.ptr(status), _lib.ptr(ws), wsb, _lib.stream_ptr())
+    m = int(dn[0])
+    return di[0, :m].cpu().numpy(), int(status[0])
+
+
+def _random_boxes(rng, n, spread=0.25):
+    ctr = rng.uniform(0.2, 0.8, (n, 2))
+    sz = rng.uniform(0.05, spread, (n, 2))
+    return np.concatenate([ctr - sz / 2, ctr + sz / 2], -1).astype(np.float32)
+
+
+@pytest.mark.parametrize('n,num_classes', [(1, 1), (31, 1), (400, 1), (3000, 3), (20000, 5)])
+def test_nms_random_boxes_vs_oracle(n, num_classes):
+    rng = np.random.default_rng(n)
+    boxes = _random_boxes(rng, n)
+    scores = rng.permutation(n).astype(np.float32) / n + 0.001
+    classes = rng.integers(0, num_classes, n)
+    got, status = _nms_raw(boxes, scores, classes, num_classes)
+    cand = oracle.BoxesDecoded(boxes, scores, classes.astype(np.int64))
+    _, want = oracle.nms_classwise(cand, num_classes, return_indices=True)
+    np.testing.assert_array_equal(got, want)
+    assert status == 0
+
+
+def test_nms_ties_max_output_and_overflow():
+    rng = np.random.default_rng(5)
+    boxes = _random_boxes(rng, 600, spread=0.08)
+    scores = np.repeat(rng.uniform(0.5, 1.0, 60).astype(np.float32), 10)  # 10-way score ties
+    rng.shuffle(scores)
+    classes = np.zeros(600, np.int64)
+    cand = oracle.BoxesDecoded(boxes, scores, classes)
+    got, _ = _nms_raw(boxes, scores, classes, 1)
+    np.testing.assert_array_equal(got, oracle.nms_classwise(cand, 1, return_indices=True)[1])  # ties -> lower index
+    got, _ = _nms_raw(boxes, scores, classes, 1, max_out=7)
+    np.testing.assert_array_equal(got, oracle.nms_classwise(cand, 1, max_output_size=7, return_indices=True)[1])
+    got, status = _nms_raw(boxes, scores, classes, 1, out_capacity=5)
+    assert got.shape[0] == 5 and status & 8
+    got, _ = _nms_raw(np.zeros((0, 4), np.float32), np.zeros((0,), np.float32), np.zeros((0,), np.int64), 4)
+    assert got.shape[0] == 0
+
+
+def test_nms_degenerate_and_flipped_boxes():
+    """tf.image.non_max_suppression normalises corner order and gives zero-area boxes IoU 0."""
+    boxes = np.array([[0.1, 0.1, 0.5, 0.5], [0.5, 0.5, 0.1, 0.1], [0.3, 0.3, 0.3, 0.6], [0.3, 0.3, 0.3, 0.6],
+                      [0.12, 0.1, 0.5, 0.52]], np.float32)
+    scores = np.array([0.9, 0.8, 0.7, 0.6, 0.5], np.float32)
+    classes = np.zeros(5, np.int64)
+    got, _ = _nms_raw(boxes, scores, classes, 1)
+    want = oracle.nms_classwise(oracle.BoxesDecoded(boxes, scores, classes), 1, return_indices=True)[1]
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got, [0, 2, 3])

@@ -1,0 +1,106 @@
+"""K2/K3 parity (GPU): fused classification + regression loss forward/backward through the C ABI
+vs the oracle's utils.process_labels_and_logits + losses.loss (and its analytic gradients) on
+the same seeded inputs.  Tolerance: 1e-5 relative (north_star), plus an absolute floor of
+1e-6 x max|reference| for the near-zero elements whose value is dominated by float32
+cancellation in the reference's own `1 - (1 - p)` ("tolerances")."""
+import numpy as np
+import pytest
+
+import helpers
+import rn_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+MODES = ['focal', 'bce_dice', 'bce', 'balanced_bce', 'balanced_bce_dice', 'focal_dice']
+
+
+def _setup(name, batch, mode):
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS[name]
+    ref = helpers.oracle_labels_batch(wl, batch)
+    cls = helpers.merge_levels(ref['cls'], 1)
+    mask = helpers.merge_levels(ref['mask'])
+    reg = helpers.merge_levels(ref['reg'], 1)
+    lab = helpers.compact_labels(cls, mask)
+    logits, regs = synthetic.head_outputs(lab, reg, wl.num_classes, seed=7 + wl.config, device='cpu')
+    boxes, classes, counts = synthetic.gt_batch(wl, batch)
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, cls_mode=mode,
+                         process_group=False)
+    path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
+    return wl, path, cls, mask, reg, logits, regs
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2)])
+def test_fused_loss_matches_oracle(name, batch, mode):
+    import torch
+    wl, path, cls, mask, reg, logits, regs = _setup(name, batch, mode)
+    out = path.loss(logits.cuda(), regs.cuda()).cpu().numpy()
+    torch.cuda.synchronize()
+    x, r = logits.numpy(), regs.numpy()
+    labels = oracle.Detection(oracle.Classification(None, cls[mask]), reg[mask], None)
+    preds = oracle.Detection(oracle.Classification(x[mask], oracle.sigmoid(x[mask])), r[mask], None)
+    cls_loss, reg_loss = oracle.loss(labels, preds, mode=mode)
+    fg = oracle.classmap_decode(cls[mask]).fg_mask
+    np.testing.assert_allclose(out[0], cls_loss, rtol=1e-5)
+    np.testing.assert_allclose(out[1], reg_loss, rtol=1e-5)
+    assert out[2] == fg.sum() and out[3] == mask.sum()
+    # gradients w.r.t. the full maps: zero on ignored anchors (boolean_mask's gradient)
+    g_ref = np.zeros_like(x)
+    g_ref[mask] = oracle.classification_loss_grad(cls[mask], x[mask], fg, mode=mode)
+    helpers.assert_close(path.dlogits.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max(),
+                         what='dlogits ' + mode)
+    gr_ref = np.zeros_like(r)
+    gr_ref[mask] = oracle.regression_loss_grad(reg[mask], r[mask], fg)
+    helpers.assert_close(path.dreg.cpu().numpy(), gr_ref, rtol=1e-5, atol=1e-6 * np.abs(gr_ref).max(), what='dreg')
+
+
+def test_loss_is_deterministic_and_forward_only_matches():
+    import torch
+    wl, path, cls, mask, reg, logits, regs = _setup('shapes', 2, 'focal')
+    lg, rg = logits.cuda(), regs.cuda()
+    a = path.loss(lg, rg).clone()
+    g1 = path.dlogits.clone()
+    b = path.loss(lg, rg).clone()
+    assert torch.equal(a, b) and torch.equal(g1, path.dlogits)
+    c = path.loss(lg, rg, want_grad=False).clone()
+    assert torch.equal(a, c)
+
+
+def test_per_level_inputs_equal_merged():
+    """Per-level [B,H,W,A,C] tensors (the reference's layout, retinanet.py:68-69) and the merged
+    buffer are the same thing to the kernels."""
+    import torch
+    wl, path, cls, mask, reg, logits, regs = _setup('shapes', 2, 'bce_dice')
+    lg, rg = logits.cuda(), regs.cuda()
+    a = path.loss(lg, rg).clone()
+    lv = {k: v.clone() for k, v in path.per_level(lg, (wl.num_classes,)).items()}
+    rv = {k: v.clone() for k, v in path.per_level(rg, (4,)).items()}
+    b = path.loss(lv, rv).clone()
+    assert torch.equal(a, b)
+
+
+def test_reference_huber_vector():
+    """losses_test.py:17-27: labels [[3],[4],[6]], logits [[1],[2],[3]], fg [T,F,T] -> 2.0.
+    The C ABI works on 4-wide rows; replicate the single column so that the mean is unchanged."""
+    import ctypes as C
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    _lib.require_cuda()
+    pred = torch.tensor([[1.] * 4, [2.] * 4, [3.] * 4], device='cuda')
+    target = torch.tensor([[3.] * 4, [4.] * 4, [6.] * 4], device='cuda')
+    fg = torch.tensor([1, 0, 1], dtype=torch.uint8, device='cuda')
+    stats = torch.zeros(8 + 3, dtype=torch.float64, device='cuda')
+    stats[1] = 2.0
+    out = torch.zeros(4, device='cuda')
+    dpred = torch.empty_like(pred)
+    ws = torch.zeros(_lib.lib.rn_loss_workspace_bytes(1), dtype=torch.uint8, device='cuda')
+    rows = _lib.rows_of([3])
+    _lib.call('rn_huber_fwd_bwd', C.byref(rows), C.byref(_lib.maps_of([pred])), C.byref(_lib.maps_of([target])),
+              C.byref(_lib.Maps()), C.byref(_lib.maps_of([fg])), C.byref(_lib.maps_of([dpred])), _lib.ptr(stats),
+              _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.call('rn_loss_finalize', 1, _lib.RN_CLS_BCE, _lib.ptr(stats), _lib.ptr(out), _lib.stream_ptr())
+    assert out[1].item() == 2.0
+    np.testing.assert_array_equal(dpred.cpu().numpy(), np.array([[-1.] * 4, [0.] * 4, [-1.] * 4]) / 8.0)
