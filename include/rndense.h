@@ -225,6 +225,13 @@ RN_API int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const 
                             const rn_maps_t* label, const rn_maps_t* fg_mask, const rn_maps_t* dpred,
                             double* d_stats, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same loss for the reference's own call shape: [rows, width] arrays of any width and a
+ * u8 fg mask [rows] (losses_test.py:17-27 uses width 1).  Reads num_fg from d_stats, writes
+ * the scalar loss to d_loss and (optional) the gradient to d_dpred. */
+RN_API int rn_huber_rows(int64_t rows, int width, const float* d_pred, const float* d_target,
+                         const uint8_t* d_fg_mask, float* d_dpred, const double* d_stats,
+                         float* d_loss, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Final scalars from the (all-reduced) stats: d_out[0] = classification loss, d_out[1] =
  * regression loss, d_out[2] = num_fg, d_out[3] = M  (losses.loss, losses.py:155-175). */
 RN_API int rn_loss_finalize(int num_classes, int mode, const double* d_stats, float* d_out, void* stream);

@@ -491,6 +491,20 @@ def process_labels_and_logits(labels, logits, levels, anchor_size_mode='tf1_int_
 # --------------------------------------------------------------------------------------
 # losses.py
 # --------------------------------------------------------------------------------------
+def _rsum(x, axis=None):
+    """tf.reduce_sum over float32 data.  TF's CPU reduction is an Eigen tree whose order is not
+    knowable here, and NumPy's axis-0 reduction is a naive sequential add whose float32 error
+    grows like sqrt(M) ulp (1e-5 relative at M ~ 1e5).  The oracle therefore accumulates in
+    float64 and rounds ONCE to float32: the correctly rounded value any good float32 reduction
+    is close to."""
+    return np.sum(np.asarray(x), axis=axis, dtype=np.float64).astype(F32)
+
+
+def _rmean(x):
+    x = np.asarray(x)
+    return F32(np.sum(x, dtype=np.float64) / max(x.size, 1)) if x.size else F32(np.nan)
+
+
 def bce_with_logits(labels, logits):
     """tf.nn.sigmoid_cross_entropy_with_logits (losses.py:107,124):
     max(x,0) - x*z + log1p(exp(-|x|)), float32."""
@@ -532,14 +546,14 @@ def focal_softmax_cross_entropy_with_logits(labels, logits, focus=2.0, alpha=0.2
 def _sums(labels, logits, axis):
     z = np.asarray(labels, F32)
     p = sigmoid(logits)
-    inter = np.sum((z * p).astype(F32), axis=axis, dtype=F32)
+    inter = _rsum((z * p).astype(F32), axis)
     return z, p, inter
 
 
 def jaccard_loss(labels, logits, smooth=1., axis=None):
     """losses.py:37-47."""
     z, p, inter = _sums(labels, logits, axis)
-    union = np.sum(z, axis=axis, dtype=F32) + np.sum(p, axis=axis, dtype=F32)
+    union = _rsum(z, axis) + _rsum(p, axis)
     with np.errstate(divide='ignore', invalid='ignore'):
         jac = (inter + F32(smooth)) / (union - inter + F32(smooth))
         return ((F32(1) - jac) * F32(smooth)).astype(F32)
@@ -548,7 +562,7 @@ def jaccard_loss(labels, logits, smooth=1., axis=None):
 def dice_loss(labels, logits, smooth=1., axis=None):
     """losses.py:50-60."""
     z, p, inter = _sums(labels, logits, axis)
-    union = np.sum(z, axis=axis, dtype=F32) + np.sum(p, axis=axis, dtype=F32)
+    union = _rsum(z, axis) + _rsum(p, axis)
     with np.errstate(divide='ignore', invalid='ignore'):
         coef = (F32(2) * inter + F32(smooth)) / (union + F32(smooth))
         return (F32(1) - coef).astype(F32)
@@ -557,7 +571,7 @@ def dice_loss(labels, logits, smooth=1., axis=None):
 def fixed_iou_loss(labels, logits, smooth=1., axis=0):
     """losses.py:63-73."""
     z, p, inter = _sums(labels, logits, axis)
-    union = np.sum(z, axis=axis, dtype=F32) + np.sum(((F32(1) - z) * p).astype(F32), axis=axis, dtype=F32)
+    union = _rsum(z, axis) + _rsum(((F32(1) - z) * p).astype(F32), axis)
     with np.errstate(divide='ignore', invalid='ignore'):
         return (F32(1) - (inter + F32(smooth)) / (union + F32(smooth))).astype(F32)
 
@@ -565,8 +579,8 @@ def fixed_iou_loss(labels, logits, smooth=1., axis=0):
 def balanced_sigmoid_cross_entropy_with_logits(labels, logits, axis=None):
     """losses.py:96-110 (weights broadcast over `axis`; no keepdims, as in the reference)."""
     z = np.asarray(labels, F32)
-    n_pos = np.sum(z, axis=axis, dtype=F32)
-    n_neg = np.sum((F32(1) - z).astype(F32), axis=axis, dtype=F32)
+    n_pos = _rsum(z, axis)
+    n_neg = _rsum((F32(1) - z).astype(F32), axis)
     with np.errstate(divide='ignore', invalid='ignore'):
         w_pos = (n_neg / (n_pos + n_neg)).astype(F32)
         w_neg = (n_pos / (n_pos + n_neg)).astype(F32)
@@ -588,14 +602,14 @@ def classification_loss(labels, logits, fg_mask, mode='bce_dice'):
     total = F32(0)
     if mode in ('focal', 'focal_dice'):
         focal = focal_sigmoid_cross_entropy_with_logits(labels, logits)
-        num_fg = np.sum(np.asarray(fg_mask).astype(F32), dtype=F32)
-        total = total + np.sum(focal, dtype=F32) / np.maximum(num_fg, F32(1.0))
+        num_fg = _rsum(np.asarray(fg_mask).astype(F32))
+        total = total + _rsum(focal) / np.maximum(num_fg, F32(1.0))
     if mode in ('bce', 'bce_dice'):
-        total = total + np.mean(bce_with_logits(labels, logits), dtype=F32)
+        total = total + _rmean(bce_with_logits(labels, logits))
     if mode in ('balanced_bce', 'balanced_bce_dice'):
-        total = total + np.mean(balanced_sigmoid_cross_entropy_with_logits(labels, logits, axis=0), dtype=F32)
+        total = total + _rmean(balanced_sigmoid_cross_entropy_with_logits(labels, logits, axis=0))
     if mode in ('bce_dice', 'balanced_bce_dice', 'focal_dice'):
-        total = total + np.mean(dice_loss(labels, logits, smooth=0., axis=0), dtype=F32)
+        total = total + _rmean(dice_loss(labels, logits, smooth=0., axis=0))
     if mode not in CLS_MODES:
         raise ValueError(mode)
     return F32(total)
@@ -617,7 +631,7 @@ def regression_loss(labels, logits, fg_mask):
     w = np.asarray(fg_mask).astype(F32).reshape(-1, 1)
     w = np.broadcast_to(w, h.shape)
     num_present = np.sum(w != 0, dtype=np.float64)
-    s = np.sum((h * w).astype(F32), dtype=F32)
+    s = _rsum((h * w).astype(F32))
     return F32(s / F32(num_present)) if num_present > 0 else F32(0)
 
 
@@ -662,21 +676,27 @@ def classification_loss_grad(labels, logits, fg_mask, mode='bce_dice', dtype=F32
     x = np.asarray(logits, T)
     m, c = z.shape
     p = (T(1) / (T(1) + np.exp(-x))).astype(T)
+    # d BCE / dx exactly as TF autodiff composes it from max(x,0) - x z + log1p(exp(-|x|)):
+    # relu'(x) - z - sign(x) e/(1+e), e = exp(-|x|)  (== p - z, but without the cancellation
+    # of `p - 1` when z = 1 and p -> 1)
+    e = np.exp(-np.abs(x)).astype(T)
+    sfrac = (e / (T(1) + e)).astype(T)
+    dbce = np.where(x >= 0, (T(1) - z) - sfrac, sfrac - z).astype(T)
     g = np.zeros_like(x, dtype=T)
     if mode in ('focal', 'focal_dice'):
         num_fg = max(float(np.sum(np.asarray(fg_mask))), 1.0)
         g = g + focal_grad(z, x, dtype=T) / T(num_fg)
     if mode in ('bce', 'bce_dice'):
-        g = g + (p - z) / T(m * c)
+        g = g + dbce / T(m * c)
     if mode in ('balanced_bce', 'balanced_bce_dice'):
-        n_pos = z.sum(0)
-        n_neg = (T(1) - z).sum(0)
+        n_pos = _rsum(z, 0).astype(T)
+        n_neg = _rsum(T(1) - z, 0).astype(T)
         with np.errstate(divide='ignore', invalid='ignore'):
             w = np.where(z == 1, n_neg / (n_pos + n_neg), n_pos / (n_pos + n_neg)).astype(T)
-        g = g + w * (p - z) / T(m * c)
+        g = g + w * dbce / T(m * c)
     if mode in ('bce_dice', 'balanced_bce_dice', 'focal_dice'):
-        inter = (z * p).sum(0)
-        union = z.sum(0) + p.sum(0)
+        inter = np.sum(z * p, 0, dtype=np.float64).astype(T)
+        union = (np.sum(z, 0, dtype=np.float64) + np.sum(p, 0, dtype=np.float64)).astype(T)
         with np.errstate(divide='ignore', invalid='ignore'):
             # d/dp [1 - 2I/U] = -2 (z U - I) / U^2 ; mean over C
             g = g + (-(T(2) * (z * union - inter) / (union * union)) * p * (T(1) - p)) / T(c)

@@ -90,6 +90,7 @@ PROTOTYPES = {
     'rn_cls_sums': (_i, [_RP, _i, _MP, _MP, _i, _vp, _vp, _sz, _vp]),
     'rn_cls_loss_fwd_bwd': (_i, [_RP, _i, _MP, _MP, _i, _i, _f, _f, _f, _MP, _vp, _vp, _sz, _vp]),
     'rn_huber_fwd_bwd': (_i, [_RP, _MP, _MP, _MP, _MP, _MP, _vp, _vp, _sz, _vp]),
+    'rn_huber_rows': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_loss_finalize': (_i, [_i, _i, _vp, _vp, _vp]),
     'rn_cls_loss_elementwise': (_i, [_i64, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     'rn_colsum_backward': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -48,14 +48,18 @@ __device__ __forceinline__ void focal_elem(float x, bool z, const LossScalars& s
   }
 }
 
-// tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log1p(exp(-|x|)); d/dx = p - z.
+// tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log1p(exp(-|x|)).  Its autodiff
+// gradient is relu'(x) - z - sign(x) e/(1+e) with e = exp(-|x|) (== p - z, minus the
+// cancellation of `p - 1`).  Also returns p = sigmoid(x) for the dice term.
 template <bool GRAD>
-__device__ __forceinline__ void bce_elem(float x, float z, float& loss, float& p_out) {
+__device__ __forceinline__ void bce_elem(float x, float z, float& loss, float& p_out, float& dx) {
   const float e = expf(-fabsf(x));
   loss = fadd(fsub(fmaxf(x, 0.0f), fmul(x, z)), log1pf(e));
   if (GRAD) {
     const float r = fdiv(1.0f, fadd(1.0f, e));
-    p_out = x >= 0.0f ? r : e * r;
+    const float s = e * r;
+    p_out = x >= 0.0f ? r : s;
+    dx = x >= 0.0f ? (1.0f - z) - s : s - z;
   }
 }
 
@@ -150,7 +154,8 @@ cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsPa
         focal_elem<true>(x[k], z[k] == 1.0f, prm.sc, loss, gr);
         g[k] = gr * inv_fg;
       } else if (MODE == RN_CLS_BCE || MODE == RN_CLS_BALANCED_BCE) {
-        bce_elem<true>(x[k], z[k], loss, p);
+        float dx = 0.0f;
+        bce_elem<true>(x[k], z[k], loss, p, dx);
         have_p = true;
         float wgt = inv_mc;
         if (MODE == RN_CLS_BALANCED_BCE) {
@@ -158,7 +163,7 @@ cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsPa
           loss *= wc;
           wgt *= wc;
         }
-        g[k] = (p - z[k]) * wgt;
+        g[k] = dx * wgt;
       }
       if (DICE) {
         if (!have_p) p = sigmoid_f32(x[k]);
@@ -369,6 +374,48 @@ huber_kernel(const __grid_constant__ Segs segs, const __grid_constant__ HuberPar
   }
 }
 
+// Same loss for [rows, width] arrays of any width with a u8 foreground mask (the reference's
+// regression_loss signature, losses.py:144-152; its own test uses width 1, losses_test.py:17-27).
+__global__ void __launch_bounds__(kLossThreads)
+huber_rows_kernel(long long rows, int width, const float* __restrict__ pred, const float* __restrict__ target,
+                  const unsigned char* __restrict__ fg_mask, float* __restrict__ dpred, const double* stats,
+                  float* loss_out, double* partials, unsigned* ticket) {
+  __shared__ double s_red[32];
+  const long long n = rows * width;
+  const double nfg = stats[RN_STAT_NUM_FG];
+  const float gscale = nfg > 0 ? (float)(1.0 / ((double)width * nfg)) : 0.0f;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    if (fg_mask[i / width]) {
+      const float e = fsub(pred[i], target[i]);
+      const float ae = fabsf(e);
+      const float q = fminf(ae, 1.0f);
+      acc += (double)fadd(0.5f * fmul(q, q), fsub(ae, q));
+      g = fminf(fmaxf(e, -1.0f), 1.0f) * gscale;
+    }
+    if (dpred) dpred[i] = g;
+  }
+  acc = block_sum(acc, s_red);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = acc;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(partials + i);
+    v = block_sum(v, s_red);
+    if (threadIdx.x == 0) {
+      *loss_out = nfg > 0 ? (float)(v / ((double)width * nfg)) : 0.0f;  // SUM_BY_NONZERO_WEIGHTS
+      *ticket = 0;
+    }
+  }
+}
+
 __global__ void loss_finalize_kernel(int C, int mode, const double* __restrict__ stats, float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double M = stats[RN_STAT_TRAINABLE], nfg = stats[RN_STAT_NUM_FG];
@@ -403,8 +450,7 @@ __global__ void cls_elementwise_kernel(long long n, int C, const float* __restri
       focal_elem<true>(x, z == 1.0f, sc, loss, grad);
     } else {
       float p;
-      bce_elem<true>(x, z, loss, p);
-      grad = p - z;
+      bce_elem<true>(x, z, loss, p, grad);
       if (mode == RN_CLS_BALANCED_BCE && w_pos) {
         const int c = (int)(i % C);
         const float w = (z == 1.0f) ? w_pos[c] : w_neg[c];
@@ -620,6 +666,23 @@ extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, co
   const unsigned grid = loss_grid(segs.start[RN_MAX_LEVELS], kLossThreads, 8);
   huber_kernel<<<grid, kLossThreads, 0, st>>>(segs, prm);
   RN_CUDA_CHECK_LAUNCH("rn_huber_fwd_bwd");
+  return RN_OK;
+}
+
+extern "C" int rn_huber_rows(int64_t rows, int width, const float* d_pred, const float* d_target,
+                             const uint8_t* d_fg_mask, float* d_dpred, const double* d_stats, float* d_loss,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+  RN_REQUIRE(rows >= 0 && width >= 1, RN_ERR_BAD_ARG, "rn_huber_rows: bad shape");
+  RN_REQUIRE(d_stats && d_loss && d_workspace, RN_ERR_BAD_ARG, "rn_huber_rows: NULL pointer");
+  RN_REQUIRE(workspace_bytes >= rn_loss_workspace_bytes(1), RN_ERR_CAPACITY, "rn_huber_rows: workspace too small");
+  RN_REQUIRE(rows == 0 || (d_pred && d_target && d_fg_mask), RN_ERR_BAD_ARG, "rn_huber_rows: NULL input");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* ticket = reinterpret_cast<unsigned*>(d_workspace);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
+  cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
+  huber_rows_kernel<<<loss_grid((long long)rows * width, kLossThreads, 8), kLossThreads, 0, st>>>(
+      rows, width, d_pred, d_target, d_fg_mask, d_dpred, d_stats, d_loss, partials, ticket);
+  RN_CUDA_CHECK_LAUNCH("rn_huber_rows");
   return RN_OK;
 }
 
