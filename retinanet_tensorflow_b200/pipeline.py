@@ -77,6 +77,7 @@ class DenseHeadPath(object):
         self.capacity = int(capacity)
         self.out_capacity = int(out_capacity if out_capacity is not None else capacity)
         self.group = process_group
+        self.stage_hook = None  # optional callable(stage_name, thunk) -> thunk(); bench.py times stages with it
         self.pyr = pyramid_for(self.image_size, self.levels, anchor_size_mode, self.names)
         self.anchors = int(self.pyr.anchors_per_image)
         self.rows_total = self.batch * self.anchors
@@ -158,6 +159,9 @@ class DenseHeadPath(object):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, group=self.group)
 
+    def _stage(self, name, fn):
+        return fn() if self.stage_hook is None else self.stage_hook(name, fn)
+
     # ---- stage 1: assignment + encoding (dataset.build_labels) ------------------------------
     def assign(self, gt_boxes, gt_classes, gt_counts):
         """gt_boxes f32 [B, max_gt, 4], gt_classes i32 [B, max_gt], gt_counts i32 [B] (device).
@@ -170,11 +174,12 @@ class DenseHeadPath(object):
         if tuple(gt_counts.shape) != (B,) or gt_counts.dtype != torch.int32:
             raise ValueError('gt_counts must be int32 [%d]' % B)
         self.stats.zero_()
-        _lib.call('rn_assign_encode', C.byref(self.pyr), B, _lib.ptr(gt_boxes.contiguous()),
-                  _lib.ptr(gt_classes.contiguous()), _lib.ptr(gt_counts.contiguous()), self.max_gt,
-                  self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched), C.byref(self._m_label),
-                  C.byref(self._m_deltas), C.byref(self._m_iou), _lib.ptr(self.stats), _lib.ptr(self.status),
-                  _lib.stream_ptr())
+        gt_boxes, gt_classes, gt_counts = gt_boxes.contiguous(), gt_classes.contiguous(), gt_counts.contiguous()
+        self._stage('assign', lambda: _lib.call(
+            'rn_assign_encode', C.byref(self.pyr), B, _lib.ptr(gt_boxes), _lib.ptr(gt_classes), _lib.ptr(gt_counts),
+            self.max_gt, self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched),
+            C.byref(self._m_label), C.byref(self._m_deltas), C.byref(self._m_iou), _lib.ptr(self.stats),
+            _lib.ptr(self.status), _lib.stream_ptr()))
         self._allreduce(self.stats)
         return self.label, self.deltas
 
@@ -198,12 +203,14 @@ class DenseHeadPath(object):
             _lib.call('rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
                       _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st)
             self._allreduce(self.stats[_lib.RN_STATS_HEADER + Cn:])
-        _lib.call('rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
-                  self.mode, self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats),
-                  _lib.ptr(self._loss_ws), self._loss_ws_bytes, st)
-        _lib.call('rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas),
-                  C.byref(self._m_label), C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats),
-                  _lib.ptr(self._huber_ws), self._huber_ws.numel(), st)
+        self._stage('cls_loss', lambda: _lib.call(
+            'rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, self.mode,
+            self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
+            self._loss_ws_bytes, st))
+        self._stage('huber', lambda: _lib.call(
+            'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
+            C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
+            self._huber_ws.numel(), st))
         self._allreduce(self.stats[_lib.RN_STAT_CLS_SUM:_lib.RN_STAT_HUBER_SUM + 1])
         _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
         return self.loss_out
@@ -212,19 +219,21 @@ class DenseHeadPath(object):
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
         m_scores, _ = self._maps(scores, self.num_classes)
         m_reg, _ = self._maps(regression, 4)
-        _lib.call('rn_decode_select', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_scores),
-                  int(scores_are_logits), C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level,
-                  self.capacity, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
-                  _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self.status),
-                  _lib.ptr(self._sel_ws), self._sel_ws_bytes, _lib.stream_ptr())
+        self._stage('select', lambda: _lib.call(
+            'rn_decode_select', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_scores),
+            int(scores_are_logits), C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level,
+            self.capacity, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
+            _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self.status), _lib.ptr(self._sel_ws),
+            self._sel_ws_bytes, _lib.stream_ptr()))
         return self.cand_count
 
     def nms(self):
-        _lib.call('rn_nms_classwise', self.batch, self.num_classes, self.capacity, _lib.ptr(self.cand_boxes),
-                  _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes), _lib.ptr(self.cand_count), self.nms_iou,
-                  self.max_output_per_class, self.out_capacity, _lib.ptr(self.det_boxes), _lib.ptr(self.det_scores),
-                  _lib.ptr(self.det_classes), _lib.ptr(self.det_index), _lib.ptr(self.det_count),
-                  _lib.ptr(self.status), _lib.ptr(self._nms_ws), self._nms_ws_bytes, _lib.stream_ptr())
+        self._stage('nms', lambda: _lib.call(
+            'rn_nms_classwise', self.batch, self.num_classes, self.capacity, _lib.ptr(self.cand_boxes),
+            _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes), _lib.ptr(self.cand_count), self.nms_iou,
+            self.max_output_per_class, self.out_capacity, _lib.ptr(self.det_boxes), _lib.ptr(self.det_scores),
+            _lib.ptr(self.det_classes), _lib.ptr(self.det_index), _lib.ptr(self.det_count), _lib.ptr(self.status),
+            _lib.ptr(self._nms_ws), self._nms_ws_bytes, _lib.stream_ptr()))
         return self.det_count
 
     def detect(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
