@@ -33,8 +33,8 @@ UNIT = 'images/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='coco', choices=['shapes', 'voc', 'coco', 'crowded'])
     ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the workload batch)')
@@ -193,7 +193,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '50'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None

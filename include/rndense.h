@@ -131,6 +131,9 @@ RN_API const char* rn_status_string(int status);
 /* number of kernels this library has launched in this process (bench.py gpu_launches) */
 RN_API int64_t rn_launch_count(void);
 RN_API int rn_set_device(int device);
+/* Process-wide switches.  "fast_focal" (default 1): use the specialised focal kernel when it
+ * applies (focal, focus == 2, compact labels, C % 4 == 0); 0 forces the generic kernel. */
+RN_API int rn_set_option(const char* name, int value);
 
 /* ---- pyramid description (host only, no launch) -------------------------------------- */
 /* levels.build_levels + the per-level constants of dataset.level_labels (dataset.py:53-57):

@@ -75,6 +75,7 @@ PROTOTYPES = {
     'rn_status_string': (C.c_char_p, [_i]),
     'rn_launch_count': (_i64, []),
     'rn_set_device': (_i, [_i]),
+    'rn_set_option': (_i, [C.c_char_p, _i]),
     'rn_pyramid_build': (_i, [_i, _i, _i, _vp, _vp, _i, _i, _PP]),
     'rn_pyramid_from_grids': (_i, [_i, _vp, _vp, _i, _PP]),
     'rn_rows_from_pyramid': (_i, [_PP, _i, _RP]),

@@ -9,6 +9,8 @@
 // and the multi-GPU exchange is one all-reduce of that vector.  Loss sums are reduced
 // warp -> block -> (per-block partials, fixed-order final pass by the last block), so results
 // are run-to-run deterministic.
+#include <string.h>
+
 #include "rn_common.cuh"
 
 namespace rn {
@@ -190,6 +192,170 @@ cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsPa
     __threadfence();
     const unsigned t = atomicAdd(prm.ticket, 1u);
     s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(prm.partials + i);
+    v = block_sum(v, s_red);
+    if (threadIdx.x == 0) {
+      prm.stats_out[RN_STAT_CLS_SUM] = v;
+      *prm.ticket = 0;
+    }
+  }
+}
+
+// ---- fast path: focal (focus == 2), compact labels, C % 4 == 0 -------------------------------------
+// The generic kernel above spends ~110 instructions per logit (IEEE divisions, libm expf/logf with
+// their special-case branches, a 64-bit division per unit) and is issue-bound at a third of the
+// HBM roofline.  This kernel keeps the reference's op sequence (p, naive 1-p, eps inside the log)
+// but evaluates each primitive with the cheapest form that stays within ~1 ulp:
+//   exp  : ex2.approx on a hi/lo-split x*log2(e)            (rel. err <= 2.4e-7)
+//   1/d  : rcp.approx + one Newton step                      (<= 1 ulp)
+//   log  : exponent/mantissa split + degree-9 minimax log1p  (rel. err <= 1.2e-7, no branches)
+// and treats every element as a negative (z = 0); the at-most-one positive element of a row is
+// recomputed afterwards on a rare path.  Row/column of a unit advance incrementally, so the
+// loop has no division.
+__device__ __forceinline__ float ex2_approx(float t) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
+__device__ __forceinline__ float rcp_newton(float d) {
+  const float r = rcp_approx(d);
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+// exp(-x), clamped so that 1 + e stays finite
+__device__ __forceinline__ float exp_neg_fast(float x) {
+  const float kL2E = 1.44269502163e+00f, kL2E_lo = 1.92596303e-08f;
+  const float t = x * -kL2E;
+  float r = fmaf(x, -kL2E, -t);   // exact rounding error of the product
+  r = fmaf(x, -kL2E_lo, r);
+  const float e = ex2_approx(fminf(t, 126.0f));
+  return fmaf(e, r * 0.693147182f, e);
+}
+// log(a) for positive normal a (here a = p_t + eps in [1e-7, 1 + 1e-7])
+__device__ __forceinline__ float log_fast(float a) {
+  const int ia = __float_as_int(a);
+  const int e = (ia - 0x3f2aaaab) & 0xff800000;
+  const float f = __int_as_float(ia - e) - 1.0f;  // mantissa in [2/3, 4/3] minus 1
+  float q = 1.402632743e-01f;
+  q = fmaf(q, f, -1.538854539e-01f);
+  q = fmaf(q, f, 1.399581283e-01f);
+  q = fmaf(q, f, -1.641595960e-01f);
+  q = fmaf(q, f, 2.001116872e-01f);
+  q = fmaf(q, f, -2.500782013e-01f);
+  q = fmaf(q, f, 3.333319724e-01f);
+  q = fmaf(q, f, -4.999993742e-01f);
+  const float r = fmaf(f * f, q, f);
+  return fmaf((float)e, 8.26295832e-08f, r);  // (e / 2^23) * ln 2
+}
+
+struct FocalFastParams {
+  Ptrs logits, label, dlogits;
+  float alpha, eps;
+  const double* stats;
+  double* stats_out;
+  double* partials;
+  unsigned* ticket;
+  int num_classes;
+  int cv;           // float4 units per row
+  int write_grad;
+};
+
+// loss and d loss/dx of one NEGATIVE element (z = 0), gradient already scaled by cg = (1-alpha)/nfg
+__device__ __forceinline__ void focal_neg_fast(float x, float eps, float cl, float cg, float& loss, float& grad) {
+  const float e = exp_neg_fast(x);
+  const float p = rcp_newton(1.0f + e);
+  const float q = 1.0f - p;     // prob_true
+  const float w = 1.0f - q;     // naive 1 - prob_true, as the reference computes it
+  const float pe = q + eps;
+  const float lg = log_fast(pe);
+  const float mod = w * w;
+  loss = (cl * mod) * lg;                                  // -(1-alpha) w^2 log(q + eps)
+  const float v = fmaf(mod, rcp_newton(pe), -2.0f * (w * lg));  // w^2/(q+eps) - 2 w log(q+eps)
+  grad = (cg * v) * (p * q);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
+  __shared__ double s_red[32];
+  const double nfg = prm.stats[RN_STAT_NUM_FG];
+  const float inv_fg = (float)(1.0 / fmax(nfg, 1.0));
+  const float cl = -(1.0f - prm.alpha);
+  const float cg = (1.0f - prm.alpha) * inv_fg;
+  LossScalars sc;
+  sc.focus = 2.0f;
+  sc.alpha = prm.alpha;
+  sc.one_minus_alpha = 1.0f - prm.alpha;
+  sc.eps = prm.eps;
+  const unsigned cv = (unsigned)prm.cv;
+  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned drow = (unsigned)(gstride / cv), dcol = (unsigned)(gstride % cv);
+  double acc = 0.0;
+
+  for (int s = 0; s < segs.num; ++s) {
+    const unsigned long long units = (unsigned long long)segs.rows[s] * cv;
+    const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
+    const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
+    float4* __restrict__ gout = reinterpret_cast<float4*>(prm.dlogits.p[s]);
+    unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    unsigned long long row = u / cv;          // one division per thread per segment
+    unsigned col = (unsigned)(u - row * cv);
+    float lsum = 0.0f;
+    int since_flush = 0;
+    for (; u < units; u += gstride) {
+      const float4 v = __ldcs(xin + u);
+      const int lab = __ldg(lab_p + row);
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lab != RN_LABEL_IGNORE) {
+        float l0, l1, l2, l3;
+        focal_neg_fast(v.x, prm.eps, cl, cg, l0, g.x);
+        focal_neg_fast(v.y, prm.eps, cl, cg, l1, g.y);
+        focal_neg_fast(v.z, prm.eps, cl, cg, l2, g.z);
+        focal_neg_fast(v.w, prm.eps, cl, cg, l3, g.w);
+        const unsigned d = (unsigned)(lab - (int)(col * 4u));
+        if (d < 4u) {  // the row's positive class sits in this unit: redo that element with z = 1
+          const float xv = d == 0 ? v.x : d == 1 ? v.y : d == 2 ? v.z : v.w;
+          float lp, gp;
+          focal_elem<true>(xv, true, sc, lp, gp);
+          gp *= inv_fg;
+          if (d == 0) { l0 = lp; g.x = gp; }
+          else if (d == 1) { l1 = lp; g.y = gp; }
+          else if (d == 2) { l2 = lp; g.z = gp; }
+          else { l3 = lp; g.w = gp; }
+        }
+        lsum += (l0 + l1) + (l2 + l3);
+      }
+      if (prm.write_grad) __stcs(gout + u, g);
+      // advance (row, col) by gstride units without dividing
+      col += dcol;
+      row += drow;
+      if (col >= cv) {
+        col -= cv;
+        row += 1;
+      }
+      if (++since_flush == 64) {  // keep the float accumulator short
+        acc += (double)lsum;
+        lsum = 0.0f;
+        since_flush = 0;
+      }
+    }
+    acc += (double)lsum;
+  }
+
+  acc = block_sum(acc, s_red);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    prm.partials[blockIdx.x] = acc;
+    __threadfence();
+    s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (s_last) {
@@ -480,6 +646,9 @@ __global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float*
     out[i] = sigmoid_f32(in[i]);
 }
 
+// rn_set_option("fast_focal", 0) forces the generic kernel (used by the parity tests to cover both)
+static int g_fast_focal = 1;
+
 static unsigned loss_grid(long long units, int threads, int per_sm) {
   long long blocks = (units + threads - 1) / threads;
   long long cap = (long long)num_sms() * per_sm;
@@ -515,6 +684,16 @@ static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaS
 }  // namespace rn
 
 using namespace rn;
+
+extern "C" int rn_set_option(const char* name, int value) {
+  RN_REQUIRE(name, RN_ERR_BAD_ARG, "rn_set_option: NULL name");
+  if (strcmp(name, "fast_focal") == 0) {
+    g_fast_focal = value != 0;
+    return RN_OK;
+  }
+  rn::set_error("rn_set_option: unknown option '%s'", name);
+  return RN_ERR_BAD_ARG;
+}
 
 extern "C" size_t rn_loss_workspace_bytes(int num_classes) {
   const size_t per_block = (size_t)(2 * (num_classes > 0 ? num_classes : 1)) * sizeof(double);
@@ -617,6 +796,24 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   RN_REQUIRE(smem <= 48 * 1024, RN_ERR_UNSUPPORTED, "rn_cls_loss_fwd_bwd: too many classes");
   cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
   const bool dense = dense_labels != 0;
+  if (base == RN_CLS_FOCAL && !dice && !dense && vec4 && focus == 2.0f && g_fast_focal) {
+    FocalFastParams fp;
+    fp.logits = prm.logits;
+    fp.label = prm.label;
+    fp.dlogits = prm.dlogits;
+    fp.alpha = alpha;
+    fp.eps = eps;
+    fp.stats = d_stats;
+    fp.stats_out = d_stats;
+    fp.partials = prm.partials;
+    fp.ticket = prm.ticket;
+    fp.num_classes = num_classes;
+    fp.cv = num_classes / 4;
+    fp.write_grad = prm.write_grad;
+    cls_focal_fast_kernel<<<grid, kLossThreads, 0, st>>>(segs, fp);
+    RN_CUDA_CHECK_LAUNCH("rn_cls_loss_fwd_bwd(fast focal)");
+    return RN_OK;
+  }
   switch (base) {
     case RN_CLS_FOCAL:
       if (dice) launch_cls2<RN_CLS_FOCAL, true>(dense, vec4, grid, smem, st, segs, prm);

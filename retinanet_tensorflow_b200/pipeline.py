@@ -21,7 +21,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, dist
 from ._pyramid import level_rows, level_shapes, pyramid_for, split_merged
 from .levels import build_levels
 
@@ -152,12 +152,8 @@ class DenseHeadPath(object):
         return dict(zip(self.names, split_merged(self.pyr, self.batch, merged, trailing)))
 
     def _allreduce(self, t):
-        """Sum `t` over the ranks (process_group=False disables; None = default group)."""
-        if self.group is False:
-            return
-        dist = torch.distributed
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(t, group=self.group)
+        """Sum a slice of the stats vector over the ranks (process_group=False disables)."""
+        dist.all_reduce_sum(t, self.group)
 
     def _stage(self, name, fn):
         return fn() if self.stage_hook is None else self.stage_hook(name, fn)

@@ -32,10 +32,21 @@ def _setup(name, batch, mode):
     return wl, path, cls, mask, reg, logits, regs
 
 
+@pytest.fixture(params=[1, 0], ids=['fast_focal', 'generic'])
+def focal_kernel(request):
+    """Run focal cases through both the specialised and the generic kernel."""
+    from retinanet_tensorflow_b200 import _lib
+    _lib.call('rn_set_option', b'fast_focal', request.param)
+    yield request.param
+    _lib.call('rn_set_option', b'fast_focal', 1)
+
+
 @pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2)])
-def test_fused_loss_matches_oracle(name, batch, mode):
+def test_fused_loss_matches_oracle(name, batch, mode, focal_kernel):
     import torch
+    if focal_kernel == 0 and (mode != 'focal' or name == 'shapes'):
+        pytest.skip('the generic kernel is what runs anyway')
     wl, path, cls, mask, reg, logits, regs = _setup(name, batch, mode)
     out = path.loss(logits.cuda(), regs.cuda()).cpu().numpy()
     torch.cuda.synchronize()
@@ -55,6 +66,31 @@ def test_fused_loss_matches_oracle(name, batch, mode):
     gr_ref = np.zeros_like(r)
     gr_ref[mask] = oracle.regression_loss_grad(reg[mask], r[mask], fg)
     helpers.assert_close(path.dreg.cpu().numpy(), gr_ref, rtol=1e-5, atol=1e-6 * np.abs(gr_ref).max(), what='dreg')
+
+
+def test_fast_focal_extreme_logits_stay_finite_and_close():
+    """Saturated logits (|x| up to 60) through the fast kernel: finite, and equal to the generic
+    kernel within the usual tolerance."""
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    wl, path, cls, mask, reg, logits, regs = _setup('voc', 1, 'focal')
+    g = torch.Generator().manual_seed(0)
+    lg = (logits + torch.randn(logits.shape, generator=g) * 12.0).cuda()
+    lg[::97, 3] = 60.0
+    lg[::89, 5] = -60.0
+    rg = regs.cuda()
+    a = path.loss(lg, rg).clone()
+    ga = path.dlogits.clone()
+    _lib.call('rn_set_option', b'fast_focal', 0)
+    try:
+        b = path.loss(lg, rg).clone()
+        gb = path.dlogits.clone()
+    finally:
+        _lib.call('rn_set_option', b'fast_focal', 1)
+    assert torch.isfinite(a).all() and torch.isfinite(ga).all()
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5)
+    helpers.assert_close(ga.cpu().numpy(), gb.cpu().numpy(), rtol=2e-5, atol=1e-6 * float(gb.abs().max()),
+                         what='fast vs generic')
 
 
 def test_loss_is_deterministic_and_forward_only_matches():
