@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
+    ap.add_argument('--opt', action='append', default=[], help='rn_set_option name=value (tuning knob)')
     ap.add_argument('--ref-budget-s', type=float, default=120.0, help='wall-clock budget of the reference arm')
     return ap.parse_args()
 
@@ -265,6 +266,9 @@ def run_b200(args):
         torch.cuda.set_device(0)
     dev = torch.device('cuda', torch.cuda.current_device())
 
+    for kv in args.opt:
+        k, v = kv.split('=')
+        _lib.call('rn_set_option', k.encode(), int(v))
     wl = synthetic.WORKLOADS[args.workload]
     batch = wl.batch if args.batch is None else args.batch
 

@@ -231,20 +231,22 @@ __device__ __forceinline__ float rcp_newton(float d) {
   const float r = rcp_approx(d);
   return fmaf(r, fmaf(-d, r, 1.0f), r);
 }
-// exp(-x), clamped so that 1 + e stays finite
+// exp(-x), clamped so that 1 + e stays finite.  The product x*log2(e) is split into its rounded
+// value and its exact rounding error (one FFMA), so the result carries only ex2.approx's error.
 __device__ __forceinline__ float exp_neg_fast(float x) {
-  const float kL2E = 1.44269502163e+00f, kL2E_lo = 1.92596303e-08f;
+  const float kL2E = 1.44269502163e+00f;
   const float t = x * -kL2E;
-  float r = fmaf(x, -kL2E, -t);   // exact rounding error of the product
-  r = fmaf(x, -kL2E_lo, r);
+  const float r = fmaf(x, -kL2E, -t);
   const float e = ex2_approx(fminf(t, 126.0f));
-  return fmaf(e, r * 0.693147182f, e);
+  return fmaf(e * r, 0.693147182f, e);
 }
-// log(a) for positive normal a (here a = p_t + eps in [1e-7, 1 + 1e-7])
+// log(a) for positive normal a (here a = p_t + eps in [1e-7, 1 + 1e-7]); no I2F (XU pipe): the
+// exponent becomes a float through the 1.5*2^23 magic constant.
 __device__ __forceinline__ float log_fast(float a) {
   const int ia = __float_as_int(a);
   const int e = (ia - 0x3f2aaaab) & 0xff800000;
   const float f = __int_as_float(ia - e) - 1.0f;  // mantissa in [2/3, 4/3] minus 1
+  const float kf = __int_as_float((e >> 23) + 0x4b400000) - 12582912.0f;
   float q = 1.402632743e-01f;
   q = fmaf(q, f, -1.538854539e-01f);
   q = fmaf(q, f, 1.399581283e-01f);
@@ -254,7 +256,7 @@ __device__ __forceinline__ float log_fast(float a) {
   q = fmaf(q, f, 3.333319724e-01f);
   q = fmaf(q, f, -4.999993742e-01f);
   const float r = fmaf(f * f, q, f);
-  return fmaf((float)e, 8.26295832e-08f, r);  // (e / 2^23) * ln 2
+  return fmaf(kf, 0.693147182f, r);
 }
 
 struct FocalFastParams {
@@ -269,86 +271,167 @@ struct FocalFastParams {
   int write_grad;
 };
 
-// loss and d loss/dx of one NEGATIVE element (z = 0), gradient already scaled by cg = (1-alpha)/nfg
-__device__ __forceinline__ void focal_neg_fast(float x, float eps, float cl, float cg, float& loss, float& grad) {
+// One NEGATIVE element (z = 0): returns w^2 log(q + eps) (the loss without its -(1-alpha) factor)
+// and the gradient scaled by cg = (1-alpha)/max(num_fg,1).
+__device__ __forceinline__ float focal_neg_fast(float x, float eps, float cg, float& grad) {
   const float e = exp_neg_fast(x);
   const float p = rcp_newton(1.0f + e);
   const float q = 1.0f - p;     // prob_true
   const float w = 1.0f - q;     // naive 1 - prob_true, as the reference computes it
   const float pe = q + eps;
   const float lg = log_fast(pe);
+  const float u = w * lg;
   const float mod = w * w;
-  loss = (cl * mod) * lg;                                  // -(1-alpha) w^2 log(q + eps)
-  const float v = fmaf(mod, rcp_newton(pe), -2.0f * (w * lg));  // w^2/(q+eps) - 2 w log(q+eps)
+  // w^2/(q+eps) - 2 w log(q+eps): both terms positive, so rcp.approx's 1e-7 is not amplified
+  const float v = fmaf(-2.0f, u, mod * rcp_approx(pe));
   grad = (cg * v) * (p * q);
+  return w * u;
 }
 
-__global__ void __launch_bounds__(kLossThreads)
+// Same for a logit known to be <= -0.70 (p < 1/3, q + eps in [2/3, 4/3]): log needs no exponent
+// split and rcp.approx alone gives p to 1 ulp.  This is the path nearly every negative takes.
+__device__ __forceinline__ float focal_neg_bulk(float x, float eps, float cg, float& grad) {
+  const float e = exp_neg_fast(x);
+  const float p = rcp_approx(1.0f + e);
+  const float q = 1.0f - p;
+  const float w = 1.0f - q;
+  const float pe = q + eps;
+  const float f = pe - 1.0f;
+  float t = 1.402632743e-01f;
+  t = fmaf(t, f, -1.538854539e-01f);
+  t = fmaf(t, f, 1.399581283e-01f);
+  t = fmaf(t, f, -1.641595960e-01f);
+  t = fmaf(t, f, 2.001116872e-01f);
+  t = fmaf(t, f, -2.500782013e-01f);
+  t = fmaf(t, f, 3.333319724e-01f);
+  t = fmaf(t, f, -4.999993742e-01f);
+  const float lg = fmaf(f * f, t, f);
+  const float u = w * lg;
+  const float v = fmaf(-2.0f, u, (w * w) * rcp_approx(pe));
+  grad = (cg * v) * (p * q);
+  return w * u;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kLossThreads, MINB)
 cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
   __shared__ double s_red[32];
   const double nfg = prm.stats[RN_STAT_NUM_FG];
   const float inv_fg = (float)(1.0 / fmax(nfg, 1.0));
-  const float cl = -(1.0f - prm.alpha);
   const float cg = (1.0f - prm.alpha) * inv_fg;
+  const float eps = prm.eps;
   LossScalars sc;
   sc.focus = 2.0f;
   sc.alpha = prm.alpha;
   sc.one_minus_alpha = 1.0f - prm.alpha;
   sc.eps = prm.eps;
   const unsigned cv = (unsigned)prm.cv;
-  const unsigned long long gstride = (unsigned long long)gridDim.x * blockDim.x;
-  const unsigned drow = (unsigned)(gstride / cv), dcol = (unsigned)(gstride % cv);
-  double acc = 0.0;
+  const unsigned gstride = gridDim.x * blockDim.x;
+  const unsigned drow = gstride / cv, dcol = gstride % cv;
+  const bool write_grad = prm.write_grad != 0;
+  double acc_neg = 0.0, acc_pos = 0.0;   // sum of w^2 log(.) over negatives; sum of positives' losses
 
   for (int s = 0; s < segs.num; ++s) {
-    const unsigned long long units = (unsigned long long)segs.rows[s] * cv;
+    const unsigned units = (unsigned)segs.rows[s] * cv;   // < 2^32, checked by the host
     const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
     const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
     float4* __restrict__ gout = reinterpret_cast<float4*>(prm.dlogits.p[s]);
-    unsigned long long u = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    unsigned long long row = u / cv;          // one division per thread per segment
-    unsigned col = (unsigned)(u - row * cv);
-    float lsum = 0.0f;
-    int since_flush = 0;
-    for (; u < units; u += gstride) {
-      const float4 v = __ldcs(xin + u);
-      const int lab = __ldg(lab_p + row);
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lab != RN_LABEL_IGNORE) {
-        float l0, l1, l2, l3;
-        focal_neg_fast(v.x, prm.eps, cl, cg, l0, g.x);
-        focal_neg_fast(v.y, prm.eps, cl, cg, l1, g.y);
-        focal_neg_fast(v.z, prm.eps, cl, cg, l2, g.z);
-        focal_neg_fast(v.w, prm.eps, cl, cg, l3, g.w);
-        const unsigned d = (unsigned)(lab - (int)(col * 4u));
-        if (d < 4u) {  // the row's positive class sits in this unit: redo that element with z = 1
-          const float xv = d == 0 ? v.x : d == 1 ? v.y : d == 2 ? v.z : v.w;
-          float lp, gp;
-          focal_elem<true>(xv, true, sc, lp, gp);
-          gp *= inv_fg;
-          if (d == 0) { l0 = lp; g.x = gp; }
-          else if (d == 1) { l1 = lp; g.y = gp; }
-          else if (d == 2) { l2 = lp; g.z = gp; }
-          else { l3 = lp; g.w = gp; }
-        }
-        lsum += (l0 + l1) + (l2 + l3);
-      }
-      if (prm.write_grad) __stcs(gout + u, g);
-      // advance (row, col) by gstride units without dividing
-      col += dcol;
-      row += drow;
+    unsigned u = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned row = u / cv;          // one division per thread per segment
+    unsigned col = u - row * cv;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four short float accumulators
+    // Two units per iteration and a one-iteration register prefetch: the loads of iteration i+1
+    // are issued before the math of iteration i, so every thread keeps four 128-bit loads in
+    // flight (Little: ~35 KB per SM must be in flight to cover HBM latency at full bandwidth).
+    // u + 4*gstride cannot wrap: units + 2^24 < 2^32 is part of the host-side check
+    unsigned col1 = col + dcol, row1 = row + drow;
+    if (col1 >= cv) {
+      col1 -= cv;
+      row1 += 1;
+    }
+    float4 nv0 = make_float4(0.f, 0.f, 0.f, 0.f), nv1 = nv0;
+    int nlab0 = RN_LABEL_IGNORE, nlab1 = RN_LABEL_IGNORE;
+    if (u < units) {
+      nv0 = __ldcs(xin + u);
+      nlab0 = __ldg(lab_p + row);
+    }
+    if (u + gstride < units) {
+      nv1 = __ldcs(xin + u + gstride);
+      nlab1 = __ldg(lab_p + row1);
+    }
+    for (; u < units; u += 2 * gstride) {
+      const unsigned u1 = u + gstride;
+      const bool has1 = u1 < units;
+      const float4 v0 = nv0, v1 = nv1;
+      const int lab0 = nlab0, lab1 = nlab1;
+      const unsigned ccol = col, ccol1 = col1;
+      // next iteration's coordinates and loads
+      col = col1 + dcol;
+      row = row1 + drow;
       if (col >= cv) {
         col -= cv;
         row += 1;
       }
-      if (++since_flush == 64) {  // keep the float accumulator short
-        acc += (double)lsum;
-        lsum = 0.0f;
-        since_flush = 0;
+      col1 = col + dcol;
+      row1 = row + drow;
+      if (col1 >= cv) {
+        col1 -= cv;
+        row1 += 1;
+      }
+      const unsigned un = u + 2 * gstride;
+      nlab0 = RN_LABEL_IGNORE;
+      nlab1 = RN_LABEL_IGNORE;
+      if (un < units) {
+        nv0 = __ldcs(xin + un);
+        nlab0 = __ldg(lab_p + row);
+      }
+      if (un + gstride < units) {
+        nv1 = __ldcs(xin + un + gstride);
+        nlab1 = __ldg(lab_p + row1);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const float4 v = half ? v1 : v0;
+        const int lab = half ? lab1 : lab0;
+        const unsigned c4 = (half ? ccol1 : ccol) * 4u;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lab != RN_LABEL_IGNORE) {
+          float l0, l1, l2, l3;
+          const unsigned d = (unsigned)(lab - (int)c4);
+          const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+          if (xmax <= -0.70f && d >= 4u) {  // bulk: four confident negatives
+            l0 = focal_neg_bulk(v.x, eps, cg, g.x);
+            l1 = focal_neg_bulk(v.y, eps, cg, g.y);
+            l2 = focal_neg_bulk(v.z, eps, cg, g.z);
+            l3 = focal_neg_bulk(v.w, eps, cg, g.w);
+          } else {
+            l0 = focal_neg_fast(v.x, eps, cg, g.x);
+            l1 = focal_neg_fast(v.y, eps, cg, g.y);
+            l2 = focal_neg_fast(v.z, eps, cg, g.z);
+            l3 = focal_neg_fast(v.w, eps, cg, g.w);
+            if (d < 4u) {  // the row's positive class sits in this unit: redo that element with z = 1
+              const float xv = d == 0 ? v.x : d == 1 ? v.y : d == 2 ? v.z : v.w;
+              float lp, gp;
+              focal_elem<true>(xv, true, sc, lp, gp);
+              gp *= inv_fg;
+              acc_pos += (double)lp;
+              if (d == 0) { l0 = 0.f; g.x = gp; }
+              else if (d == 1) { l1 = 0.f; g.y = gp; }
+              else if (d == 2) { l2 = 0.f; g.z = gp; }
+              else { l3 = 0.f; g.w = gp; }
+            }
+          }
+          a0 += l0;
+          a1 += l1;
+          a2 += l2;
+          a3 += l3;
+        }
+        if (write_grad && (half == 0 || has1)) __stcs(gout + (half ? u1 : u), g);
       }
     }
-    acc += (double)lsum;
+    acc_neg += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
   }
+  double acc = acc_pos - (double)(1.0f - prm.alpha) * acc_neg;   // loss = -(1-alpha) w^2 log(q+eps)
 
   acc = block_sum(acc, s_red);
   __shared__ bool s_last;
@@ -648,6 +731,22 @@ __global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float*
 
 // rn_set_option("fast_focal", 0) forces the generic kernel (used by the parity tests to cover both)
 static int g_fast_focal = 1;
+static int g_focal_minb = 4;  // resident CTAs per SM the fast focal kernel is compiled for (4 or 5)
+
+// Persistent grid: exactly the number of CTAs that are resident at once (one full wave), so a
+// grid-stride loop never runs a partially filled second wave.
+template <typename K>
+static unsigned persistent_grid(K kernel, int threads, size_t smem, long long work_items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  long long blocks = (long long)num_sms() * per_sm;
+  if (blocks > kMaxLossBlocks) blocks = kMaxLossBlocks;
+  const long long need = (work_items + threads - 1) / threads;
+  if (blocks > need) blocks = need;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
 
 static unsigned loss_grid(long long units, int threads, int per_sm) {
   long long blocks = (units + threads - 1) / threads;
@@ -689,6 +788,10 @@ extern "C" int rn_set_option(const char* name, int value) {
   RN_REQUIRE(name, RN_ERR_BAD_ARG, "rn_set_option: NULL name");
   if (strcmp(name, "fast_focal") == 0) {
     g_fast_focal = value != 0;
+    return RN_OK;
+  }
+  if (strcmp(name, "focal_min_blocks") == 0) {
+    g_focal_minb = value;
     return RN_OK;
   }
   rn::set_error("rn_set_option: unknown option '%s'", name);
@@ -796,7 +899,10 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   RN_REQUIRE(smem <= 48 * 1024, RN_ERR_UNSUPPORTED, "rn_cls_loss_fwd_bwd: too many classes");
   cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
   const bool dense = dense_labels != 0;
-  if (base == RN_CLS_FOCAL && !dice && !dense && vec4 && focus == 2.0f && g_fast_focal) {
+  bool fits32 = true;  // the fast kernel indexes float4 units with 32-bit integers
+  for (int i = 0; i < rows->num_segments; ++i)
+    if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
+  if (base == RN_CLS_FOCAL && !dice && !dense && vec4 && focus == 2.0f && g_fast_focal && fits32) {
     FocalFastParams fp;
     fp.logits = prm.logits;
     fp.label = prm.label;
@@ -810,7 +916,13 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     fp.num_classes = num_classes;
     fp.cv = num_classes / 4;
     fp.write_grad = prm.write_grad;
-    cls_focal_fast_kernel<<<grid, kLossThreads, 0, st>>>(segs, fp);
+    if (g_focal_minb >= 5) {
+      const unsigned fgrid = persistent_grid(cls_focal_fast_kernel<5>, kLossThreads, 0, (units + 1) / 2);
+      cls_focal_fast_kernel<5><<<fgrid, kLossThreads, 0, st>>>(segs, fp);
+    } else {
+      const unsigned fgrid = persistent_grid(cls_focal_fast_kernel<4>, kLossThreads, 0, (units + 1) / 2);
+      cls_focal_fast_kernel<4><<<fgrid, kLossThreads, 0, st>>>(segs, fp);
+    }
     RN_CUDA_CHECK_LAUNCH("rn_cls_loss_fwd_bwd(fast focal)");
     return RN_OK;
   }

@@ -89,8 +89,15 @@ def test_fast_focal_extreme_logits_stay_finite_and_close():
         _lib.call('rn_set_option', b'fast_focal', 1)
     assert torch.isfinite(a).all() and torch.isfinite(ga).all()
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5)
-    helpers.assert_close(ga.cpu().numpy(), gb.cpu().numpy(), rtol=2e-5, atol=1e-6 * float(gb.abs().max()),
+    ga, gb, x = ga.cpu().numpy(), gb.cpu().numpy(), lg.cpu().numpy()
+    assert np.linalg.norm((ga - gb).astype(np.float64)) <= 1e-5 * np.linalg.norm(gb.astype(np.float64))
+    # Elementwise outside saturation.  For x > 9 the reference's own `1 - p` is quantised in steps
+    # of 6e-8 that are > 0.05 % of its value (a 1-ulp change of p moves the result by that much on
+    # ANY implementation), so only a loose bound is meaningful there.
+    sat = x > 9.0
+    helpers.assert_close(np.where(sat, 0, ga), np.where(sat, 0, gb), rtol=2e-5, atol=1e-6 * float(np.abs(gb).max()),
                          what='fast vs generic')
+    helpers.assert_close(ga[sat], gb[sat], rtol=0.2, atol=1e-6 * float(np.abs(gb).max()), what='saturated')
 
 
 def test_loss_is_deterministic_and_forward_only_matches():
