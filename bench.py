@@ -402,7 +402,7 @@ def run_b200(args):
             'assign': batch * (24 * A + 20 * wl.max_gt),
             'cls_loss': cls_bytes,
             'huber': batch * A * 20,                  # label + dreg (+32 B per positive, ~1%)
-            'select': batch * A * 4 * C,
+            'select': None if path.fused_select_supported() else batch * A * 4 * C,  # fused: finalize only
             'nms': None,
         }
         kernels = {}
@@ -431,6 +431,7 @@ def run_b200(args):
                          'alg_bytes_per_launch': cls_bytes, 'ms_per_launch': stage_ms['cls_loss'],
                          'peak_source': peak_src},
             'kernels': kernels,
+            'fused_loss_select': bool(path.fused_select_supported()),
             'cpu_baseline': cpu_baseline,
             'check': {'class_loss': loss_vals[0], 'regr_loss': loss_vals[1], 'num_fg': loss_vals[2],
                       'candidates': cand_total, 'detections': det_total},

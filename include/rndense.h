@@ -295,6 +295,29 @@ RN_API int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_classes,
                             int32_t* d_cand_anchor, int32_t* d_cand_count, uint32_t* d_status,
                             void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Second half of rn_decode_select on its own: order the (unordered) candidates a selection pass
+ * left in the workspace, optionally drop duplicate anchors (dedup != 0, needed after
+ * rn_cls_loss_select), apply the per-level top-k, decode / gather the boxes. */
+RN_API int rn_select_finalize(const rn_pyramid_t* pyr, int batch, const rn_maps_t* regs,
+                              int regs_are_deltas, int topk_per_level, int capacity, int dedup,
+                              float* d_cand_boxes, float* d_cand_scores, int32_t* d_cand_classes,
+                              int32_t* d_cand_anchor, int32_t* d_cand_count, void* d_workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* Training step with detections from the same logits (train.py:218-220 + 68-75): ONE pass over
+ * the logits computes the focal loss forward + backward (as rn_cls_loss_fwd_bwd) AND pre-selects
+ * the detection candidates (as the first half of rn_decode_select with logits as scores), so
+ * the [rows, C] tensor is read once instead of twice.  Follow with rn_select_finalize(dedup=1).
+ * Available when rn_fused_select_supported() != 0 (focal, focus == 2, compact labels,
+ * C % 4 == 0, < 2^32 float4 per level); 0 < score_thr < 1. */
+RN_API int rn_fused_select_supported(int num_classes, int mode, float focus, const rn_rows_t* rows);
+RN_API int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
+                              const rn_maps_t* label, int mode, float focus, float alpha, float eps,
+                              const rn_maps_t* dlogits, double* d_stats, void* d_loss_workspace,
+                              size_t loss_workspace_bytes, float score_thr, int capacity,
+                              int32_t* d_cand_count, uint32_t* d_status, void* d_select_workspace,
+                              size_t select_workspace_bytes, void* stream);
+
 RN_API size_t rn_nms_workspace_bytes(int batch, int num_classes, int capacity);
 
 /* utils.nms_classwise + utils.nms (utils.py:198-220): per class greedy NMS with

@@ -101,6 +101,9 @@ PROTOTYPES = {
     'rn_classmap_fg': (_i, [_i64, _i, _vp, _f, _vp, _vp]),
     'rn_select_workspace_bytes': (_sz, [_i, _i]),
     'rn_decode_select': (_i, [_PP, _i, _i, _MP, _i, _MP, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'rn_select_finalize': (_i, [_PP, _i, _MP, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'rn_fused_select_supported': (_i, [_i, _i, _f, _RP]),
+    'rn_cls_loss_select': (_i, [_RP, _i, _MP, _MP, _i, _f, _f, _f, _MP, _vp, _vp, _sz, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     'rn_nms_workspace_bytes': (_sz, [_i, _i, _i]),
     'rn_nms_classwise': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -270,6 +270,7 @@ struct FinalizeParams {
   int regs_are_deltas;
   int capacity;
   int topk;
+  int dedup;
   const int32_t* ws_anchor;
   const float* ws_score;
   const int32_t* ws_class;
@@ -283,14 +284,28 @@ struct FinalizeParams {
   int32_t* count;             // in: appended, out: final
 };
 
+// Count entries of key[0..n) whose `bit` is clear (CTA-wide); result in every thread.
+__device__ int count_kept(const unsigned long long* key, int n, int bit, int* s_cnt) {
+  if (threadIdx.x == 0) *s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += ((key[i] >> bit) & 1ull) == 0;
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(s_cnt, c);
+  __syncthreads();
+  const int r = *s_cnt;
+  __syncthreads();
+  return r;
+}
+
 __global__ void __launch_bounds__(kSortThreads)
 cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const __grid_constant__ FinalizeParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_cnt;
   const int b = blockIdx.x;
-  const int n = min(prm.count[b], prm.capacity);
+  const int n_in = min(max(prm.count[b], 0), prm.capacity);
   const size_t base = (size_t)b * prm.capacity;
-  const unsigned n_pad = max(next_pow2((unsigned)n), 2u);
+  const unsigned n_pad = max(next_pow2((unsigned)n_in), 2u);
   unsigned long long* key;
   unsigned* pos;
   if (n_pad <= (unsigned)kSortSmemElems) {
@@ -302,16 +317,48 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
   }
   // 1) ascending anchor index == the reference's (level, y, x, a) order
   for (unsigned i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    key[i] = i < (unsigned)n ? (unsigned long long)(unsigned)prm.ws_anchor[base + i] : ~0ull;
+    key[i] = i < (unsigned)n_in ? (unsigned long long)(unsigned)prm.ws_anchor[base + i] : ~0ull;
     pos[i] = i;
   }
   __syncthreads();
   bitonic_sort_pairs(key, pos, n_pad);
+  int n = n_in;
 
-  int n_final = n;
+  if (prm.dedup) {
+    // 1b) The fused loss+select pass appends one entry per firing float4 UNIT, so an anchor with
+    // several classes above the threshold appears more than once: keep its best entry (max
+    // probability, then lowest class == the first argmax of utils.py:185-186).
+    bool mine = false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned a = (unsigned)key[i];
+      if (i > 0 && (unsigned)key[i - 1] == a) continue;   // not the head of its group
+      int best = i, j = i + 1;
+      float bs = prm.ws_score[base + pos[i]];
+      int bc = prm.ws_class[base + pos[i]];
+      for (; j < n && (unsigned)key[j] == a; ++j) {
+        const float sj = prm.ws_score[base + pos[j]];
+        const int cj = prm.ws_class[base + pos[j]];
+        if (sj > bs || (sj == bs && cj < bc)) {
+          best = j;
+          bs = sj;
+          bc = cj;
+        }
+      }
+      if (j > i + 1) {
+        mine = true;
+        for (int t = i; t < j; ++t)
+          if (t != best) key[t] |= 1ull << 62;   // dropped duplicate: sorts behind every kept entry
+      }
+    }
+    if (__syncthreads_or(mine)) {
+      bitonic_sort_pairs(key, pos, n_pad);
+      n = count_kept(key, n, 62, &s_cnt);
+    }
+  }
+
   if (prm.topk > 0) {
     // 2) per-level top-k (extension, not in the reference): within each level's contiguous range
-    // sort by (score desc, anchor asc), drop everything past k, then restore anchor order.
+    // rank by (score desc, anchor asc), drop everything past k, then restore anchor order.
     bool any = false;
     for (int l = 0; l < pyr.num_levels; ++l) {
       const unsigned lo_a = (unsigned)pyr.level[l].anchor_offset;
@@ -327,7 +374,7 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
       if (end - start <= prm.topk) continue;
       any = true;
       __syncthreads();
-      // rank of element i within the level by (score desc, anchor asc); O(m^2 / threads), rare path
+      // O(m^2 / threads) ranking; only runs for levels that actually exceed k
       for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
         const float si = prm.ws_score[base + pos[i]];
         int rank = 0;
@@ -335,25 +382,19 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
           const float sj = prm.ws_score[base + pos[j]];
           rank += (sj > si) || (sj == si && j < i);
         }
-        if (rank >= prm.topk) key[i] |= 1ull << 63;  // mark dropped: sorts behind every kept entry
+        if (rank >= prm.topk) key[i] |= 1ull << 63;
       }
       __syncthreads();
     }
     __syncthreads();
     if (any) {
       bitonic_sort_pairs(key, pos, n_pad);
-      if (threadIdx.x == 0) s_cnt = 0;
-      __syncthreads();
-      int c = 0;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) c += (key[i] >> 63) == 0;
-      c = warp_sum(c);
-      if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
-      __syncthreads();
-      n_final = s_cnt;
+      n = count_kept(key, n, 63, &s_cnt);
     }
   }
+
   // 3) outputs
-  for (int i = threadIdx.x; i < n_final; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned p = pos[i];
     const int anchor = prm.ws_anchor[base + p];
     prm.out_scores[base + i] = prm.ws_score[base + p];
@@ -373,7 +414,7 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
     prm.out_boxes[base + i] = d;
   }
   __syncthreads();
-  if (threadIdx.x == 0) prm.count[b] = n_final;
+  if (threadIdx.x == 0) prm.count[b] = n;
 }
 
 // ---- NMS ------------------------------------------------------------------------------------------
@@ -513,54 +554,51 @@ __global__ void __launch_bounds__(kNmsWarps * 32) nms_greedy_kernel(const __grid
 }
 
 __global__ void __launch_bounds__(256) nms_compact_kernel(const __grid_constant__ NmsParams prm) {
-  __shared__ int s_off[1025];
+  extern __shared__ int s_off[];  // [C + 1] exclusive prefix of the per-class kept counts
   const int b = blockIdx.x;
   const int C = prm.num_classes;
   const int* kc = prm.kept_count + (size_t)b * C;
   const int* seg = prm.seg + (size_t)b * (C + 1);
   const size_t base = (size_t)b * prm.capacity;
   const size_t obase = (size_t)b * prm.out_capacity;
-  // exclusive prefix over classes (C is small; chunked serial scan by thread 0)
-  __shared__ int s_total;
-  if (threadIdx.x == 0) s_total = 0;
+  // prefix over classes: warp 0 scans C in chunks of 32
+  if (threadIdx.x < 32) {
+    int carry = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + (int)threadIdx.x;
+      const int v = c < C ? kc[c] : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)threadIdx.x >= o) incl += t;
+      }
+      if (c < C) s_off[c] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_off[C] = carry;
+  }
   __syncthreads();
-  for (int c0 = 0; c0 < C; c0 += 1024) {
-    const int cn = min(1024, C - c0);
-    if (threadIdx.x == 0) {
-      int acc = s_total;
-      for (int c = 0; c < cn; ++c) {
-        s_off[c] = acc;
-        acc += kc[c0 + c];
-      }
-      s_off[cn] = acc;
+  const int total = s_off[C];
+  const int n_out = min(total, prm.out_capacity);
+  // one output slot per thread: class by binary search in the prefix (class-major order)
+  for (int o = threadIdx.x; o < n_out; o += blockDim.x) {
+    int lo = 0, hi = C - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= o) lo = mid; else hi = mid - 1;
     }
-    __syncthreads();
-    for (int c = 0; c < cn; ++c) {
-      const int off = s_off[c], m = s_off[c + 1] - s_off[c];
-      const int st = seg[c0 + c];
-      for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        const int o = off + j;
-        if (o < prm.out_capacity) {
-          const unsigned rank = prm.kept[base + st + j];
-          const unsigned ci = prm.perm[base + rank];
-          prm.det_boxes[obase + o] = prm.boxes[base + ci];
-          prm.det_scores[obase + o] = prm.scores[base + ci];
-          prm.det_classes[obase + o] = prm.classes[base + ci];
-          prm.det_index[obase + o] = (int)ci;
-        }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_total = s_off[cn];
-    __syncthreads();
+    const int j = o - s_off[lo];
+    const unsigned rank = prm.kept[base + seg[lo] + j];
+    const unsigned ci = prm.perm[base + rank];
+    prm.det_boxes[obase + o] = prm.boxes[base + ci];
+    prm.det_scores[obase + o] = prm.scores[base + ci];
+    prm.det_classes[obase + o] = prm.classes[base + ci];
+    prm.det_index[obase + o] = (int)ci;
   }
   if (threadIdx.x == 0) {
-    int tot = s_total;
-    if (tot > prm.out_capacity) {
-      tot = prm.out_capacity;
-      if (prm.status) atomicOr(prm.status, RN_FLAG_DET_OVERFLOW);
-    }
-    prm.det_count[b] = tot;
+    if (total > prm.out_capacity && prm.status) atomicOr(prm.status, RN_FLAG_DET_OVERFLOW);
+    prm.det_count[b] = n_out;
   }
 }
 
@@ -707,14 +745,38 @@ extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_clas
   else launch_select_lpr<1>(lpr, upl, (unsigned)blocks, st, segs, sp);
   RN_CUDA_CHECK_LAUNCH("rn_decode_select(select)");
 
+  return rn_select_finalize(pyr, batch, regs, regs_are_deltas, topk_per_level, capacity, 0, d_cand_boxes,
+                            d_cand_scores, d_cand_classes, d_cand_anchor, d_cand_count, d_workspace, workspace_bytes,
+                            stream);
+}
+
+extern "C" int rn_select_finalize(const rn_pyramid_t* pyr, int batch, const rn_maps_t* regs, int regs_are_deltas,
+                                  int topk_per_level, int capacity, int dedup, float* d_cand_boxes,
+                                  float* d_cand_scores, int32_t* d_cand_classes, int32_t* d_cand_anchor,
+                                  int32_t* d_cand_count, void* d_workspace, size_t workspace_bytes, void* stream) {
+  RN_REQUIRE(pyr && maps_present(regs), RN_ERR_BAD_ARG, "rn_select_finalize: NULL input");
+  RN_REQUIRE(d_cand_boxes && d_cand_scores && d_cand_classes && d_cand_anchor && d_cand_count && d_workspace,
+             RN_ERR_BAD_ARG, "rn_select_finalize: NULL output");
+  RN_REQUIRE(batch >= 0 && capacity >= 1, RN_ERR_BAD_ARG, "rn_select_finalize: bad sizes");
+  RN_REQUIRE(workspace_bytes >= rn_select_workspace_bytes(batch, capacity), RN_ERR_CAPACITY,
+             "rn_select_finalize: workspace too small");
+  RN_REQUIRE(((uintptr_t)d_cand_boxes & 15) == 0, RN_ERR_BAD_ARG, "d_cand_boxes must be 16-byte aligned");
+  if (batch == 0) return RN_OK;
+  for (int l = 0; l < pyr->num_levels; ++l)
+    RN_REQUIRE(regs->p[l] && ((uintptr_t)regs->p[l] & 15) == 0, RN_ERR_BAD_ARG,
+               "regs map of level %d missing or not 16-byte aligned", l);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)batch * capacity;
+  char* ws = (char*)d_workspace;
   FinalizeParams fp;
   fp.regs = make_ptrs(regs);
   fp.regs_are_deltas = regs_are_deltas;
   fp.capacity = capacity;
   fp.topk = topk_per_level;
-  fp.ws_anchor = sp.ws_anchor;
-  fp.ws_score = sp.ws_score;
-  fp.ws_class = sp.ws_class;
+  fp.dedup = dedup;
+  fp.ws_anchor = (const int32_t*)ws; ws += align256(n * 4);
+  fp.ws_score = (const float*)ws; ws += align256(n * 4);
+  fp.ws_class = (const int32_t*)ws; ws += align256(n * 4);
   fp.pad = host_next_pow2((unsigned)capacity);
   fp.g_key = nullptr;
   fp.g_pos = nullptr;
@@ -730,7 +792,7 @@ extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_clas
   const size_t smem = sort_smem_bytes(capacity);
   cudaFuncSetAttribute(cand_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
   cand_finalize_kernel<<<batch, kSortThreads, smem, st>>>(*pyr, batch, fp);
-  RN_CUDA_CHECK_LAUNCH("rn_decode_select(finalize)");
+  RN_CUDA_CHECK_LAUNCH("rn_select_finalize");
   return RN_OK;
 }
 
@@ -805,7 +867,7 @@ extern "C" int rn_nms_classwise(int batch, int num_classes, int capacity, const 
   const long long pairs = (long long)batch * num_classes;
   nms_greedy_kernel<<<(unsigned)((pairs + kNmsWarps - 1) / kNmsWarps), kNmsWarps * 32, greedy_smem, st>>>(p);
   RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(greedy)");
-  nms_compact_kernel<<<batch, 256, 0, st>>>(p);
+  nms_compact_kernel<<<batch, 256, (size_t)(num_classes + 1) * sizeof(int), st>>>(p);
   RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(compact)");
   return RN_OK;
 }

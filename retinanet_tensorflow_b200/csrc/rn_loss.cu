@@ -11,6 +11,8 @@
 // are run-to-run deterministic.
 #include <string.h>
 
+#include <cmath>
+
 #include "rn_common.cuh"
 
 namespace rn {
@@ -269,6 +271,16 @@ struct FocalFastParams {
   int num_classes;
   int cv;           // float4 units per row
   int write_grad;
+  // fused candidate pre-selection (rn_cls_loss_select): the same pass also finds the anchors whose
+  // max class probability exceeds `thr` (utils.boxes_decode, utils.py:183-190)
+  float sel_trigger;   // logit below which sigmoid(x) <= thr for sure
+  float sel_thr;
+  int sel_images, sel_capacity;
+  int32_t* sel_anchor;   // [B, capacity] unordered, one entry per firing UNIT (deduplicated later)
+  float* sel_score;
+  int32_t* sel_class;
+  int32_t* sel_count;    // [B]
+  uint32_t* status;
 };
 
 // One NEGATIVE element (z = 0): returns w^2 log(q + eps) (the loss without its -(1-alpha) factor)
@@ -312,7 +324,7 @@ __device__ __forceinline__ float focal_neg_bulk(float x, float eps, float cg, fl
   return w * u;
 }
 
-template <int MINB>
+template <int MINB, bool SELECT>
 __global__ void __launch_bounds__(kLossThreads, MINB)
 cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
   __shared__ double s_red[32];
@@ -365,6 +377,8 @@ cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__
       const float4 v0 = nv0, v1 = nv1;
       const int lab0 = nlab0, lab1 = nlab1;
       const unsigned ccol = col, ccol1 = col1;
+      const unsigned srow = row, srow1 = row1;
+      (void)srow; (void)srow1;
       // next iteration's coordinates and loads
       col = col1 + dcol;
       row = row1 + drow;
@@ -395,10 +409,42 @@ cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__
         const int lab = half ? lab1 : lab0;
         const unsigned c4 = (half ? ccol1 : ccol) * 4u;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        if (SELECT && xmax > prm.sel_trigger && (half == 0 || has1)) {
+          // rare: some class of this anchor may exceed the score threshold.  Evaluate the exact
+          // sigmoid for those elements and append the unit's best (max prob, first class).
+          const float xs[4] = {v.x, v.y, v.z, v.w};
+          float bp = -INFINITY;
+          int bc = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (xs[k] > prm.sel_trigger) {
+              const float pk = sigmoid_f32(xs[k]);
+              if (pk > bp) {
+                bp = pk;
+                bc = (int)c4 + k;
+              }
+            }
+          }
+          if (bp > prm.sel_thr) {
+            const unsigned r = half ? srow1 : srow;
+            const unsigned per_image = (unsigned)(segs.rows[s] / prm.sel_images);
+            const unsigned bimg = r / per_image;
+            const int anchor = (int)(segs.start[s] / prm.sel_images) + (int)(r - bimg * per_image);
+            const int slot = atomicAdd(prm.sel_count + bimg, 1);
+            if (slot < prm.sel_capacity) {
+              const size_t o = (size_t)bimg * prm.sel_capacity + slot;
+              prm.sel_anchor[o] = anchor;
+              prm.sel_score[o] = bp;
+              prm.sel_class[o] = bc;
+            } else if (prm.status) {
+              atomicOr(prm.status, RN_FLAG_CAND_OVERFLOW);
+            }
+          }
+        }
         if (lab != RN_LABEL_IGNORE) {
           float l0, l1, l2, l3;
           const unsigned d = (unsigned)(lab - (int)c4);
-          const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
           if (xmax <= -0.70f && d >= 4u) {  // bulk: four confident negatives
             l0 = focal_neg_bulk(v.x, eps, cg, g.x);
             l1 = focal_neg_bulk(v.y, eps, cg, g.y);
@@ -748,6 +794,9 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem, long long wo
   return (unsigned)blocks;
 }
 
+static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, bool select, long long units,
+                             cudaStream_t st);
+
 static unsigned loss_grid(long long units, int threads, int per_sm) {
   long long blocks = (units + threads - 1) / threads;
   long long cap = (long long)num_sms() * per_sm;
@@ -778,6 +827,24 @@ static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaS
     launch_cls<MODE, DICE, true>(vec4, grid, smem, st, segs, prm);
   else
     launch_cls<MODE, DICE, false>(vec4, grid, smem, st, segs, prm);
+}
+
+static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, bool select, long long units,
+                             cudaStream_t st) {
+  const long long work = (units + 1) / 2;
+#define RN_LAUNCH_FF(MINB, SEL)                                                                     \
+  do {                                                                                              \
+    const unsigned g = persistent_grid(cls_focal_fast_kernel<MINB, SEL>, kLossThreads, 0, work);    \
+    cls_focal_fast_kernel<MINB, SEL><<<g, kLossThreads, 0, st>>>(segs, fp);                         \
+  } while (0)
+  if (g_focal_minb >= 5) {
+    if (select) RN_LAUNCH_FF(5, true); else RN_LAUNCH_FF(5, false);
+  } else {
+    if (select) RN_LAUNCH_FF(4, true); else RN_LAUNCH_FF(4, false);
+  }
+#undef RN_LAUNCH_FF
+  RN_CUDA_CHECK_LAUNCH("focal fast kernel");
+  return RN_OK;
 }
 
 }  // namespace rn
@@ -904,6 +971,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
   if (base == RN_CLS_FOCAL && !dice && !dense && vec4 && focus == 2.0f && g_fast_focal && fits32) {
     FocalFastParams fp;
+    memset(&fp, 0, sizeof(fp));
     fp.logits = prm.logits;
     fp.label = prm.label;
     fp.dlogits = prm.dlogits;
@@ -916,15 +984,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     fp.num_classes = num_classes;
     fp.cv = num_classes / 4;
     fp.write_grad = prm.write_grad;
-    if (g_focal_minb >= 5) {
-      const unsigned fgrid = persistent_grid(cls_focal_fast_kernel<5>, kLossThreads, 0, (units + 1) / 2);
-      cls_focal_fast_kernel<5><<<fgrid, kLossThreads, 0, st>>>(segs, fp);
-    } else {
-      const unsigned fgrid = persistent_grid(cls_focal_fast_kernel<4>, kLossThreads, 0, (units + 1) / 2);
-      cls_focal_fast_kernel<4><<<fgrid, kLossThreads, 0, st>>>(segs, fp);
-    }
-    RN_CUDA_CHECK_LAUNCH("rn_cls_loss_fwd_bwd(fast focal)");
-    return RN_OK;
+    return launch_focal_fast(segs, fp, false, units, st);
   }
   switch (base) {
     case RN_CLS_FOCAL:
@@ -945,6 +1005,76 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   }
   RN_CUDA_CHECK_LAUNCH("rn_cls_loss_fwd_bwd");
   return RN_OK;
+}
+
+extern "C" int rn_fused_select_supported(int num_classes, int mode, float focus, const rn_rows_t* rows) {
+  if (!rows || num_classes % 4 != 0 || (mode & 15) != RN_CLS_FOCAL || (mode & RN_CLS_DICE_FLAG) || focus != 2.0f ||
+      !g_fast_focal)
+    return 0;
+  for (int i = 0; i < rows->num_segments; ++i)
+    if ((unsigned long long)rows->rows[i] * (num_classes / 4) + (1ull << 24) >= (1ull << 32)) return 0;
+  return 1;
+}
+
+extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
+                                  const rn_maps_t* label, int mode, float focus, float alpha, float eps,
+                                  const rn_maps_t* dlogits, double* d_stats, void* d_loss_workspace,
+                                  size_t loss_workspace_bytes, float score_thr, int capacity, int32_t* d_cand_count,
+                                  uint32_t* d_status, void* d_select_workspace, size_t select_workspace_bytes,
+                                  void* stream) {
+  int rc = check_rows(rows, "rn_cls_loss_select");
+  if (rc) return rc;
+  RN_REQUIRE(maps_present(logits) && maps_present(label) && d_stats && d_loss_workspace && d_select_workspace &&
+                 d_cand_count,
+             RN_ERR_BAD_ARG, "rn_cls_loss_select: NULL input");
+  RN_REQUIRE(rn_fused_select_supported(num_classes, mode, focus, rows), RN_ERR_UNSUPPORTED,
+             "rn_cls_loss_select: needs focal (focus 2), compact labels, C %% 4 == 0 and < 2^32 float4 per level; "
+             "use rn_cls_loss_fwd_bwd + rn_decode_select");
+  RN_REQUIRE(rows->images >= 1 && capacity >= 1, RN_ERR_BAD_ARG, "rn_cls_loss_select: bad images/capacity");
+  RN_REQUIRE(score_thr > 0.f && score_thr < 1.f, RN_ERR_BAD_ARG, "rn_cls_loss_select: score_thr must be in (0, 1)");
+  RN_REQUIRE(loss_workspace_bytes >= rn_loss_workspace_bytes(num_classes), RN_ERR_CAPACITY,
+             "rn_cls_loss_select: loss workspace too small");
+  RN_REQUIRE(select_workspace_bytes >= rn_select_workspace_bytes(rows->images, capacity), RN_ERR_CAPACITY,
+             "rn_cls_loss_select: select workspace too small");
+  const bool grad = maps_present(dlogits);
+  RN_REQUIRE(aligned16(logits, rows->num_segments) && (!grad || aligned16(dlogits, rows->num_segments)),
+             RN_ERR_BAD_ARG, "rn_cls_loss_select: maps must be 16-byte aligned");
+  for (int i = 0; i < rows->num_segments; ++i)
+    RN_REQUIRE(rows->rows[i] % rows->images == 0, RN_ERR_BAD_SHAPE, "rows[%d] is not a multiple of images", i);
+  const Segs segs = make_segs(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  FocalFastParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.logits = make_ptrs(logits);
+  fp.label = make_ptrs(label);
+  fp.dlogits = make_ptrs(grad ? dlogits : nullptr);
+  fp.alpha = alpha;
+  fp.eps = eps;
+  fp.stats = d_stats;
+  fp.stats_out = d_stats;
+  fp.ticket = reinterpret_cast<unsigned*>(d_loss_workspace);
+  fp.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_loss_workspace) + 256);
+  fp.num_classes = num_classes;
+  fp.cv = num_classes / 4;
+  fp.write_grad = grad ? 1 : 0;
+  // sigmoid(x) > thr needs x > logit(thr); leave a margin for the float32 sigmoid's rounding
+  const double lg = std::log((double)score_thr / (1.0 - (double)score_thr));
+  fp.sel_trigger = (float)(lg - 1e-3 * (1.0 + std::fabs(lg)));
+  fp.sel_thr = score_thr;
+  fp.sel_images = rows->images;
+  fp.sel_capacity = capacity;
+  const size_t n = (size_t)rows->images * capacity;
+  const size_t chunk = (n * 4 + 255) & ~(size_t)255;  // same carving as rn_decode_select
+  char* ws = (char*)d_select_workspace;
+  fp.sel_anchor = (int32_t*)ws;
+  fp.sel_score = (float*)(ws + chunk);
+  fp.sel_class = (int32_t*)(ws + 2 * chunk);
+  fp.sel_count = d_cand_count;
+  fp.status = d_status;
+  cudaMemsetAsync(fp.ticket, 0, sizeof(unsigned), st);
+  cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * rows->images, st);
+  const long long units = segs.start[RN_MAX_LEVELS] * (long long)fp.cv;
+  return launch_focal_fast(segs, fp, true, units, st);
 }
 
 extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const rn_maps_t* target,

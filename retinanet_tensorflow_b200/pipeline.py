@@ -211,6 +211,48 @@ class DenseHeadPath(object):
         _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
         return self.loss_out
 
+    # ---- stages 2+3 fused: one pass over the logits for the loss AND the candidate selection --
+    def fused_select_supported(self):
+        return bool(_lib.lib.rn_fused_select_supported(self.num_classes, self.mode, self.focus, C.byref(self.rows))) \
+            and 0.0 < self.score_thr < 1.0
+
+    def loss_and_select(self, logits, regression, want_grad=True):
+        """`loss()` and `select()` on the same logits with the [rows, C] tensor read ONCE: the
+        focal kernel also pre-selects the anchors whose best class probability exceeds score_thr
+        (training step that also produces detections, train.py:218-220 + 68-75)."""
+        if not self.fused_select_supported():
+            self.loss(logits, regression, want_grad)
+            self.select(logits, regression)
+            return self.loss_out, self.cand_count
+        m_logits, _ = self._maps(logits, self.num_classes)
+        m_reg, _ = self._maps(regression, 4)
+        st = _lib.stream_ptr()
+        Cn = self.num_classes
+        if want_grad:
+            if self.dlogits is None:
+                self.dlogits = torch.empty((self.rows_total, Cn), dtype=torch.float32, device=self.device)
+                self.dreg = torch.empty((self.rows_total, 4), dtype=torch.float32, device=self.device)
+            m_dlogits = self._merged_maps(self.dlogits, 4 * Cn)
+            m_dreg = self._merged_maps(self.dreg, 16)
+        else:
+            m_dlogits, m_dreg = _lib.Maps(), _lib.Maps()
+        self._stage('cls_loss', lambda: _lib.call(
+            'rn_cls_loss_select', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode,
+            self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
+            self._loss_ws_bytes, self.score_thr, self.capacity, _lib.ptr(self.cand_count), _lib.ptr(self.status),
+            _lib.ptr(self._sel_ws), self._sel_ws_bytes, st))
+        self._stage('huber', lambda: _lib.call(
+            'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
+            C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
+            self._huber_ws.numel(), st))
+        self._allreduce(self.stats[_lib.RN_STAT_CLS_SUM:_lib.RN_STAT_HUBER_SUM + 1])
+        _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
+        self._stage('select', lambda: _lib.call(
+            'rn_select_finalize', C.byref(self.pyr), self.batch, C.byref(m_reg), 1, self.topk_per_level,
+            self.capacity, 1, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
+            _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self._sel_ws), self._sel_ws_bytes, st))
+        return self.loss_out, self.cand_count
+
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
         m_scores, _ = self._maps(scores, self.num_classes)
@@ -238,10 +280,16 @@ class DenseHeadPath(object):
         return self.det_boxes, self.det_scores, self.det_classes, self.det_count
 
     # ---- one whole step of the hot path -----------------------------------------------------
-    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression):
+    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True):
+        """assign -> loss fwd+bwd -> decode/select/NMS.  With `fused` (default) and a supported
+        configuration the loss kernel also does the candidate selection (logits read once)."""
         self.assign(gt_boxes, gt_classes, gt_counts)
-        self.loss(logits, regression)
-        self.detect(logits, regression)
+        if fused and self.fused_select_supported():
+            self.loss_and_select(logits, regression)
+        else:
+            self.loss(logits, regression)
+            self.select(logits, regression)
+        self.nms()
         return self.loss_out, self.det_count
 
     def check_status(self, ignore=0):

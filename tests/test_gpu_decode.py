@@ -130,6 +130,49 @@ def test_fused_select_from_logits_and_deltas(name, batch):
         assert lv_rows == path.anchors and ref_scores.shape[0] == path.rows_total
 
 
+@pytest.mark.parametrize('name,batch', [('voc', 2), ('coco', 2)])
+def test_fused_loss_and_select_equals_separate_passes(name, batch):
+    """rn_cls_loss_select (+ rn_select_finalize with dedup) must give exactly the loss, gradients,
+    candidates and detections of rn_cls_loss_fwd_bwd followed by rn_decode_select."""
+    import torch
+    wl, path, logits, regs = _case(name, batch, capacity=8192)
+    assert path.fused_select_supported()
+    # make several classes of the same anchor fire, inside one float4 unit and across units,
+    # including exact probability ties (first class must win)
+    lv = logits.view(-1, wl.num_classes)
+    lv[5, 0:3] = torch.tensor([2.0, 3.0, 2.5], device='cuda')
+    lv[77, 1] = 4.0
+    lv[77, 9] = 4.0
+    lv[77, 17] = 3.0
+    lv[123, 6] = 30.0
+    lv[123, 2] = 40.0   # both saturate to probability 1.0 -> tie in probability space, class 2 wins
+    path.loss(logits, regs)
+    path.select(logits, regs)
+    path.nms()
+    want = {k: getattr(path, k).clone() for k in ('loss_out', 'dlogits', 'dreg', 'cand_count', 'cand_anchor',
+                                                  'cand_scores', 'cand_classes', 'cand_boxes', 'det_count',
+                                                  'det_index', 'det_boxes')}
+    for k in ('dlogits', 'cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes', 'det_index', 'det_boxes'):
+        getattr(path, k).zero_()
+    path.loss_and_select(logits, regs)
+    path.nms()
+    torch.cuda.synchronize()
+    path.check_status()
+    assert torch.equal(path.loss_out, want['loss_out']) and torch.equal(path.dlogits, want['dlogits'])
+    assert torch.equal(path.dreg, want['dreg'])
+    assert torch.equal(path.cand_count, want['cand_count']) and torch.equal(path.det_count, want['det_count'])
+    for b in range(batch):
+        n, m = int(want['cand_count'][b]), int(want['det_count'][b])
+        for k in ('cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes'):
+            assert torch.equal(getattr(path, k)[b, :n], want[k][b, :n]), k
+        for k in ('det_index', 'det_boxes'):
+            assert torch.equal(getattr(path, k)[b, :m], want[k][b, :m]), k
+    cls5 = path.cand_classes[0][path.cand_anchor[0] == 5]
+    assert cls5.numel() == 1 and int(cls5) == 1     # argmax of [2.0, 3.0, 2.5]
+    b77 = 77 % path.anchors
+    assert int(path.cand_classes[77 // path.anchors][path.cand_anchor[77 // path.anchors] == b77]) == 1
+
+
 def test_topk_per_level_prefilter():
     """Extension (not in the reference): k best per (image, level), identity for large k."""
     import torch
