@@ -151,6 +151,11 @@ class DenseHeadPath(object):
         """Reference-shaped views `[B, H, W, A, ...]` keyed 'P3'.. of a merged buffer."""
         return dict(zip(self.names, split_merged(self.pyr, self.batch, merged, trailing)))
 
+    @staticmethod
+    def per_level_static(pyr, batch, merged, width):
+        """Per-level `[B, H, W, A, width]` views of a merged buffer for an explicit pyramid/batch."""
+        return split_merged(pyr, batch, merged, (width,))
+
     def _allreduce(self, t):
         """Sum a slice of the stats vector over the ranks (process_group=False disables)."""
         dist.all_reduce_sum(t, self.group)
