@@ -1,0 +1,177 @@
+"""Edge cases of the path on the GPU: flip (augmentation.py), ragged / empty ground truth,
+capacity overflow, candidate lists larger than the shared-memory sort, class counts that are
+not a multiple of four, extreme thresholds."""
+import numpy as np
+import pytest
+
+import helpers
+import rn_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_flip_reference_vector():
+    """augmentation_test.py:7-45 (positional 4-tuple signature is stale; semantics valid)."""
+    import torch
+    from retinanet_tensorflow_b200 import augmentation
+    sample = {
+        'image': np.array([[1, 2], [3, 4]]),
+        'detection': {
+            'classifications': {'P3': np.array([[[1], [2]], [[3], [4]]])},
+            'regressions': {'P3': np.array([[[[0., 0., .5, .5]], [[.25, .25, .5, .5]]],
+                                            [[[1., 1., .5, .5]], [[.75, .75, .25, .25]]]], np.float32)},
+        },
+        'trainable_masks': {'P3': np.array([[[True], [False]], [[False], [True]]])},
+    }
+    out = augmentation.flip(sample)
+    np.testing.assert_array_equal(out['image'].cpu().numpy(), [[2, 1], [4, 3]])
+    np.testing.assert_array_equal(out['detection']['classifications']['P3'].cpu().numpy(), [[[2], [1]], [[4], [3]]])
+    np.testing.assert_array_equal(out['detection']['regressions']['P3'].cpu().numpy(),
+                                  [[[[.25, -.25, .5, .5]], [[0., -0., .5, .5]]],
+                                   [[[.75, -.75, .25, .25]], [[1., -1., .5, .5]]]])
+    np.testing.assert_array_equal(out['trainable_masks']['P3'].cpu().numpy(), [[[False], [True]], [[True], [False]]])
+
+
+def test_flip_compact_batch_matches_oracle():
+    import torch
+    from retinanet_tensorflow_b200 import augmentation, synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['shapes']
+    boxes, classes, counts = synthetic.gt_batch(wl, 2)
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 2, wl.max_gt, process_group=False)
+    path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
+    lab, dl = augmentation.flip_compact(path.pyr, 2, path.label, path.deltas)
+    lab_lv = path.per_level(path.label)
+    dl_lv = path.per_level(path.deltas, (4,))
+    got_lab = path.per_level(lab)
+    got_dl = path.per_level(dl, (4,))
+    for pn in path.names:
+        for b in range(2):
+            sample = {'detection': {'classifications': {pn: lab_lv[pn][b].cpu().numpy()[..., None]},
+                                    'regressions': {pn: dl_lv[pn][b].cpu().numpy()}},
+                      'trainable_masks': {pn: lab_lv[pn][b].cpu().numpy() != -2}}
+            want = oracle.flip(sample)
+            np.testing.assert_array_equal(got_lab[pn][b].cpu().numpy(), want['detection']['classifications'][pn][..., 0])
+            np.testing.assert_array_equal(got_dl[pn][b].cpu().numpy(), want['detection']['regressions'][pn])
+    # flipping twice is the identity
+    lab2, dl2 = augmentation.flip_compact(path.pyr, 2, lab, dl)
+    assert torch.equal(lab2, path.label) and torch.equal(dl2, path.deltas)
+
+
+def test_ragged_and_empty_ground_truth():
+    """Counts 0 / 1 / max in one batch: padding rows never participate; the empty image is
+    all-background and flagged (the reference asserts >= 1 box, inferred.py:30)."""
+    import torch
+    from retinanet_tensorflow_b200 import _lib, synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['voc']
+    boxes, classes, counts = synthetic.gt_batch(wl, 3)
+    counts[:] = [0, 1, wl.max_gt]
+    b2, c2 = synthetic.gt_for_image(wl, 2)
+    rng = np.random.default_rng(0)
+    reps = -(-wl.max_gt // b2.shape[0])
+    boxes[2] = np.tile(b2, (reps, 1))[:wl.max_gt]
+    classes[2] = np.tile(c2, reps)[:wl.max_gt]
+    boxes[0] = rng.uniform(0.1, 0.9, boxes[0].shape)   # garbage in the padding of the empty image
+    boxes[1, 1:] = 0.5
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 3, wl.max_gt, keep_iou=True, process_group=False)
+    path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
+    lab = path.per_level(path.label)
+    mat = path.per_level(path.matched)
+    status = int(path.status.item())
+    assert status & _lib.RN_FLAG_EMPTY_GT
+    with pytest.raises(AssertionError):
+        path.check_status()
+    levels = oracle.build_levels()
+    for b in (1, 2):
+        n = counts[b]
+        o_cls, o_reg, o_mask = oracle.build_labels(helpers.image_size_of(wl), classes[b, :n], boxes[b, :n], levels,
+                                                   wl.num_classes)
+        for pn in levels:
+            want = helpers.compact_labels(o_cls[pn].reshape(-1, wl.num_classes), o_mask[pn].reshape(-1))
+            np.testing.assert_array_equal(lab[pn][b].cpu().numpy().reshape(-1), want)
+    for pn in levels:
+        assert int((lab[pn][0] != -1).sum()) == 0 and int((mat[pn][0] != -1).sum()) == 0
+
+
+def test_candidate_overflow_flag_and_large_lists():
+    """score_thr so low that every anchor fires: (a) capacity overflow is flagged and the output
+    is truncated, (b) with enough capacity the > 16384-entry global-memory sort path returns
+    exactly the oracle's candidates."""
+    import torch
+    from retinanet_tensorflow_b200 import _lib, synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['shapes']
+    boxes, classes, counts = synthetic.gt_batch(wl, 1)
+    for cap in (1000, 50000):
+        path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 1, wl.max_gt, score_thr=0.001, capacity=cap,
+                             process_group=False)
+        path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
+        logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=5, device='cuda')
+        probs = torch.sigmoid(logits)
+        path.select(probs, regs, scores_are_logits=False)
+        torch.cuda.synchronize()
+        status = int(path.status.item())
+        n = int(path.cand_count[0])
+        p = probs.cpu().numpy()
+        fg = p.max(-1) > np.float32(0.001)
+        if cap == 1000:
+            assert status & _lib.RN_FLAG_CAND_OVERFLOW and n == cap
+        else:
+            assert status == 0 and n == fg.sum() and n > 16384
+            np.testing.assert_array_equal(path.cand_anchor[0, :n].cpu().numpy(), np.nonzero(fg)[0])
+            np.testing.assert_array_equal(path.cand_scores[0, :n].cpu().numpy(), p.max(-1)[fg])
+            np.testing.assert_array_equal(path.cand_classes[0, :n].cpu().numpy(), p.argmax(-1)[fg])
+            path.nms()
+            cand = oracle.BoxesDecoded(path.cand_boxes[0, :n].cpu().numpy(), path.cand_scores[0, :n].cpu().numpy(),
+                                       path.cand_classes[0, :n].cpu().numpy().astype(np.int64))
+            _, want = oracle.nms_classwise(cand, wl.num_classes, return_indices=True)
+            m = int(path.det_count[0])
+            np.testing.assert_array_equal(path.det_index[0, :m].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('num_classes', [1, 5, 7, 12])
+def test_odd_class_counts(num_classes):
+    """C not a multiple of 4 takes the scalar kernels; C = 12 the vector ones."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.Workload('odd', 9, 160, 224, num_classes, 6, 2)
+    ref = helpers.oracle_labels_batch(wl, 2)
+    cls = helpers.merge_levels(ref['cls'], 1)
+    mask = helpers.merge_levels(ref['mask'])
+    reg = helpers.merge_levels(ref['reg'], 1)
+    lab = helpers.compact_labels(cls, mask)
+    logits, regs = synthetic.head_outputs(lab, reg, num_classes, seed=3, device='cpu')
+    boxes, classes, counts = synthetic.gt_batch(wl, 2)
+    for mode in ('focal', 'bce_dice'):
+        path = DenseHeadPath((wl.image_h, wl.image_w), num_classes, 2, wl.max_gt, cls_mode=mode, process_group=False)
+        path.step(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda(),
+                  logits.cuda(), regs.cuda())
+        np.testing.assert_array_equal(path.label.cpu().numpy(), lab)
+        x, r = logits.numpy(), regs.numpy()
+        labels = oracle.Detection(oracle.Classification(None, cls[mask]), reg[mask], None)
+        preds = oracle.Detection(oracle.Classification(x[mask], oracle.sigmoid(x[mask])), r[mask], None)
+        cl, rl = oracle.loss(labels, preds, mode=mode)
+        out = path.loss_out.cpu().numpy()
+        np.testing.assert_allclose(out[:2], [cl, rl], rtol=1e-5)
+        fg = oracle.classmap_decode(cls[mask]).fg_mask
+        g_ref = np.zeros_like(x)
+        g_ref[mask] = oracle.classification_loss_grad(cls[mask], x[mask], fg, mode=mode)
+        helpers.assert_close(path.dlogits.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max(),
+                             what='dlogits C=%d %s' % (num_classes, mode))
+        # detections against the oracle fed with the GPU's own probabilities
+        probs = torch.sigmoid(logits.cuda())
+
+
+def test_zero_batch_and_argument_errors():
+    import torch
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    path = DenseHeadPath((128, 128), 4, 1, 4, process_group=False)
+    with pytest.raises(ValueError):
+        path.assign(torch.zeros((1, 3, 4), device='cuda'), torch.zeros((1, 4), dtype=torch.int32, device='cuda'),
+                    torch.ones((1,), dtype=torch.int32, device='cuda'))
+    with pytest.raises(ValueError):
+        path.loss(torch.zeros((7, 4), device='cuda'), torch.zeros((path.rows_total, 4), device='cuda'))
+    with pytest.raises(ValueError):
+        DenseHeadPath((128, 128), 4, 1, 4, cls_mode='nope', process_group=False)
