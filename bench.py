@@ -307,7 +307,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # per-kernel CUDA events (on the launching stream) for the roofline object
-    stage_events = {k: [] for k in ('assign', 'cls_loss', 'huber', 'select', 'nms')}
+    stage_events = {k: [] for k in ('assign', 'cls_sums', 'cls_loss', 'huber', 'select', 'nms')}
     record = {'on': False}
 
     def timed(name, fn):
@@ -400,6 +400,7 @@ def run_b200(args):
         cls_bytes = batch * A * (8 * C + 4)          # read logits + write dlogits + read label
         bytes_per_kernel = {
             'assign': batch * (24 * A + 20 * wl.max_gt),
+            'cls_sums': batch * A * (4 * C + 4),
             'cls_loss': cls_bytes,
             'huber': batch * A * 20,                  # label + dreg (+32 B per positive, ~1%)
             'select': None if path.fused_select_supported() else batch * A * 4 * C,  # fused: finalize only

@@ -285,7 +285,7 @@ struct FocalFastParams {
 
 // One NEGATIVE element (z = 0): returns w^2 log(q + eps) (the loss without its -(1-alpha) factor)
 // and the gradient scaled by cg = (1-alpha)/max(num_fg,1).
-__device__ __forceinline__ float focal_neg_fast(float x, float eps, float cg, float& grad) {
+__device__ __forceinline__ float focal_neg_fast(float x, float eps, float cg, float& grad, float& pq) {
   const float e = exp_neg_fast(x);
   const float p = rcp_newton(1.0f + e);
   const float q = 1.0f - p;     // prob_true
@@ -296,13 +296,14 @@ __device__ __forceinline__ float focal_neg_fast(float x, float eps, float cg, fl
   const float mod = w * w;
   // w^2/(q+eps) - 2 w log(q+eps): both terms positive, so rcp.approx's 1e-7 is not amplified
   const float v = fmaf(-2.0f, u, mod * rcp_approx(pe));
-  grad = (cg * v) * (p * q);
+  pq = p * q;
+  grad = (cg * v) * pq;
   return w * u;
 }
 
 // Same for a logit known to be <= -0.70 (p < 1/3, q + eps in [2/3, 4/3]): log needs no exponent
 // split and rcp.approx alone gives p to 1 ulp.  This is the path nearly every negative takes.
-__device__ __forceinline__ float focal_neg_bulk(float x, float eps, float cg, float& grad) {
+__device__ __forceinline__ float focal_neg_bulk(float x, float eps, float cg, float& grad, float& pq) {
   // x <= -0.70: the rounding error of x*log2(e) adds at most |x| * 6e-8 relative to e (3e-7 at
   // the prior logit), so the exact-product correction of exp_neg_fast is not needed here.
   const float e = ex2_approx(fminf(x * -1.44269502163e+00f, 126.0f));
@@ -320,16 +321,64 @@ __device__ __forceinline__ float focal_neg_bulk(float x, float eps, float cg, fl
   const float lg = fmaf(f * f, t, f);
   const float u = w * lg;
   const float v = fmaf(-2.0f, u, (w * w) * rcp_approx(pe));
-  grad = (cg * v) * (p * q);
+  pq = p * q;
+  grad = (cg * v) * pq;
   return w * u;
 }
 
-template <int MINB, bool SELECT>
+// BCE of a confident negative (x <= -0.70, z = 0): loss = log1p(e^x) by a one-sided minimax
+// polynomial on e in [0, 0.5] (7.9e-8 relative), p = e / (1 + e) = d loss / dx.
+__device__ __forceinline__ float bce_neg_bulk(float x, float& p) {
+  const float e = ex2_approx(x * 1.44269502163e+00f);   // exp(x) < 0.5
+  p = e * rcp_approx(1.0f + e);
+  float t = -2.785309963e-02f;
+  t = fmaf(t, e, 8.751634508e-02f);
+  t = fmaf(t, e, -1.473636031e-01f);
+  t = fmaf(t, e, 1.960214078e-01f);
+  t = fmaf(t, e, -2.495450228e-01f);
+  t = fmaf(t, e, 3.333081305e-01f);
+  t = fmaf(t, e, -4.999995232e-01f);
+  return fmaf(e * e, t, e);
+}
+
+// MODE: RN_CLS_FOCAL (focus 2) | RN_CLS_BCE | RN_CLS_BALANCED_BCE | RN_CLS_NONE; DICE adds the dice
+// gradient (z A_c + B_c) p (1-p).  Compact labels, C % 4 == 0.
+template <int MODE, bool DICE, int MINB, bool SELECT>
 __global__ void __launch_bounds__(kLossThreads, MINB)
-cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
+cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
+  extern __shared__ __align__(16) float s_tab[];   // [4][C]: w_neg, w_pos, dice A, dice B (when needed)
   __shared__ double s_red[32];
+  constexpr bool kTables = DICE || MODE == RN_CLS_BALANCED_BCE;
+  const int C = prm.num_classes;
+  const float* s_wneg = s_tab;
+  const float* s_wpos = s_tab + C;
+  const float* s_da = s_tab + 2 * C;
+  const float* s_db = s_tab + 3 * C;
   const double nfg = prm.stats[RN_STAT_NUM_FG];
+  const double M = prm.stats[RN_STAT_TRAINABLE];
   const float inv_fg = (float)(1.0 / fmax(nfg, 1.0));
+  const float inv_mc = M > 0 ? (float)(1.0 / (M * (double)C)) : 0.0f;
+  if (kTables) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double npos = prm.stats[RN_STAT_NPOS(c)];
+      float wn = 1.0f, wp = 1.0f, da = 0.0f, db = 0.0f;
+      if (MODE == RN_CLS_BALANCED_BCE) {  // losses.py:99-103, axis=0
+        wp = (float)((M - npos) / M);
+        wn = (float)(npos / M);
+      }
+      if (DICE) {  // d/dp [1 - 2I/U] / C = z A + B,  A = -2/(C U), B = 2 I/(C U^2)
+        const double I = prm.stats[RN_STAT_INTER(C, c)];
+        const double U = npos + prm.stats[RN_STAT_PSUM(C, c)];
+        da = (float)(-2.0 / ((double)C * U));
+        db = (float)(2.0 * I / ((double)C * U * U));
+      }
+      s_tab[c] = wn;
+      s_tab[C + c] = wp;
+      s_tab[2 * C + c] = da;
+      s_tab[3 * C + c] = db;
+    }
+    __syncthreads();
+  }
   const float cg = (1.0f - prm.alpha) * inv_fg;
   const float eps = prm.eps;
   LossScalars sc;
@@ -445,26 +494,86 @@ cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__
         if (lab != RN_LABEL_IGNORE) {
           float l0, l1, l2, l3;
           const unsigned d = (unsigned)(lab - (int)c4);
-          if (xmax <= -0.70f && d >= 4u) {  // bulk: four confident negatives
-            l0 = focal_neg_bulk(v.x, eps, cg, g.x);
-            l1 = focal_neg_bulk(v.y, eps, cg, g.y);
-            l2 = focal_neg_bulk(v.z, eps, cg, g.z);
-            l3 = focal_neg_bulk(v.w, eps, cg, g.w);
+          const bool bulk = xmax <= -0.70f && d >= 4u;   // four confident negatives
+          if constexpr (MODE == RN_CLS_FOCAL) {
+            float pq0 = 0.f, pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;
+            if (bulk) {
+              l0 = focal_neg_bulk(v.x, eps, cg, g.x, pq0);
+              l1 = focal_neg_bulk(v.y, eps, cg, g.y, pq1);
+              l2 = focal_neg_bulk(v.z, eps, cg, g.z, pq2);
+              l3 = focal_neg_bulk(v.w, eps, cg, g.w, pq3);
+            } else {
+              l0 = focal_neg_fast(v.x, eps, cg, g.x, pq0);
+              l1 = focal_neg_fast(v.y, eps, cg, g.y, pq1);
+              l2 = focal_neg_fast(v.z, eps, cg, g.z, pq2);
+              l3 = focal_neg_fast(v.w, eps, cg, g.w, pq3);
+              if (d < 4u) {  // the row's positive class sits in this unit: redo that element with z = 1
+                const float xv = d == 0 ? v.x : d == 1 ? v.y : d == 2 ? v.z : v.w;
+                float lp, gp;
+                focal_elem<true>(xv, true, sc, lp, gp);
+                gp *= inv_fg;
+                acc_pos += (double)lp;
+                if (DICE) gp += s_da[c4 + d] * (d == 0 ? pq0 : d == 1 ? pq1 : d == 2 ? pq2 : pq3);
+                if (d == 0) { l0 = 0.f; g.x = gp; }
+                else if (d == 1) { l1 = 0.f; g.y = gp; }
+                else if (d == 2) { l2 = 0.f; g.z = gp; }
+                else { l3 = 0.f; g.w = gp; }
+              }
+            }
+            if (DICE) {
+              const float4 db = *reinterpret_cast<const float4*>(s_db + c4);
+              g.x = fmaf(db.x, pq0, g.x);
+              g.y = fmaf(db.y, pq1, g.y);
+              g.z = fmaf(db.z, pq2, g.z);
+              g.w = fmaf(db.w, pq3, g.w);
+            }
           } else {
-            l0 = focal_neg_fast(v.x, eps, cg, g.x);
-            l1 = focal_neg_fast(v.y, eps, cg, g.y);
-            l2 = focal_neg_fast(v.z, eps, cg, g.z);
-            l3 = focal_neg_fast(v.w, eps, cg, g.w);
-            if (d < 4u) {  // the row's positive class sits in this unit: redo that element with z = 1
-              const float xv = d == 0 ? v.x : d == 1 ? v.y : d == 2 ? v.z : v.w;
-              float lp, gp;
-              focal_elem<true>(xv, true, sc, lp, gp);
-              gp *= inv_fg;
-              acc_pos += (double)lp;
-              if (d == 0) { l0 = 0.f; g.x = gp; }
-              else if (d == 1) { l1 = 0.f; g.y = gp; }
-              else if (d == 2) { l2 = 0.f; g.z = gp; }
-              else { l3 = 0.f; g.w = gp; }
+            // BCE / balanced BCE / none, optional dice
+            float4 wn = make_float4(1.f, 1.f, 1.f, 1.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE == RN_CLS_BALANCED_BCE) wn = *reinterpret_cast<const float4*>(s_wneg + c4);
+            if (DICE) db = *reinterpret_cast<const float4*>(s_db + c4);
+            if (bulk) {
+              float p0, p1, p2, p3;
+              l0 = bce_neg_bulk(v.x, p0);
+              l1 = bce_neg_bulk(v.y, p1);
+              l2 = bce_neg_bulk(v.z, p2);
+              l3 = bce_neg_bulk(v.w, p3);
+              if (MODE == RN_CLS_NONE) {
+                l0 = l1 = l2 = l3 = 0.f;
+              } else {
+                const float k0 = inv_mc * wn.x, k1 = inv_mc * wn.y, k2 = inv_mc * wn.z, k3 = inv_mc * wn.w;
+                g.x = p0 * k0; g.y = p1 * k1; g.z = p2 * k2; g.w = p3 * k3;
+                if (MODE == RN_CLS_BALANCED_BCE) { l0 *= wn.x; l1 *= wn.y; l2 *= wn.z; l3 *= wn.w; }
+              }
+              if (DICE) {
+                g.x = fmaf(db.x, p0 * (1.0f - p0), g.x);
+                g.y = fmaf(db.y, p1 * (1.0f - p1), g.y);
+                g.z = fmaf(db.z, p2 * (1.0f - p2), g.z);
+                g.w = fmaf(db.w, p3 * (1.0f - p3), g.w);
+              }
+            } else {
+              const float xs[4] = {v.x, v.y, v.z, v.w};
+              float ls[4], gs[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float z = (d == (unsigned)k) ? 1.0f : 0.0f;
+                float loss = 0.f, pk = 0.f, dx = 0.f;
+                bce_elem<true>(xs[k], z, loss, pk, dx);
+                float gk = 0.f;
+                if (MODE == RN_CLS_NONE) {
+                  loss = 0.f;
+                } else {
+                  float wk = 1.0f;
+                  if (MODE == RN_CLS_BALANCED_BCE) wk = z == 1.0f ? s_wpos[c4 + k] : s_wneg[c4 + k];
+                  loss *= wk;
+                  gk = dx * (inv_mc * wk);
+                }
+                if (DICE) gk += (z * s_da[c4 + k] + s_db[c4 + k]) * (pk * (1.0f - pk));
+                ls[k] = loss;
+                gs[k] = gk;
+              }
+              l0 = ls[0]; l1 = ls[1]; l2 = ls[2]; l3 = ls[3];
+              g = make_float4(gs[0], gs[1], gs[2], gs[3]);
             }
           }
           a0 += l0;
@@ -477,7 +586,8 @@ cls_focal_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__
     }
     acc_neg += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
   }
-  double acc = acc_pos - (double)(1.0f - prm.alpha) * acc_neg;   // loss = -(1-alpha) w^2 log(q+eps)
+  // focal: negatives accumulated w^2 log(q+eps), loss = -(1-alpha) * that; BCE modes: plain sum
+  double acc = MODE == RN_CLS_FOCAL ? acc_pos - (double)(1.0f - prm.alpha) * acc_neg : acc_pos + acc_neg;
 
   acc = block_sum(acc, s_red);
   __shared__ bool s_last;
@@ -550,7 +660,13 @@ __global__ void __launch_bounds__(1024) cls_sums_kernel(const __grid_constant__ 
       }
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const float p = sigmoid_f32(x[k]);
+        float p;
+        if (x[k] <= -0.70f) {  // same bulk formula as cls_fast_kernel: p = e / (1 + e), e = exp(x)
+          const float e = ex2_approx(x[k] * 1.44269502163e+00f);
+          p = e * rcp_approx(1.0f + e);
+        } else {
+          p = sigmoid_f32(x[k]);
+        }
         ai[k] += (double)(z[k] * p);
         ap[k] += (double)p;
       }
@@ -575,6 +691,89 @@ __global__ void __launch_bounds__(1024) cls_sums_kernel(const __grid_constant__ 
     const unsigned t = atomicAdd(prm.ticket, 1u);
     s_last = (t == gridDim.x - 1);
   }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+      double v = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(prm.partials + (size_t)b * 2 * C + j);
+      prm.stats_out[RN_STATS_HEADER + C + j] = v;  // INTER block then PSUM block
+    }
+    if (threadIdx.x == 0) *prm.ticket = 0;
+  }
+}
+
+// Fast variant for compact labels and C % 4 == 0: thread (tx, ty) owns the float4 column tx of the
+// rows ty, ty + RY, ...; four rows per iteration with all loads issued first; float partials per
+// class flushed to double every iteration.
+template <int UNROLL>
+__global__ void __launch_bounds__(512) cls_sums_fast_kernel(const __grid_constant__ Segs segs,
+                                                           const __grid_constant__ SumsParams prm) {
+  extern __shared__ double s_acc[];  // [ry][2C]
+  const int C = prm.num_classes;
+  const unsigned cv = (unsigned)prm.cv;
+  const unsigned tx = threadIdx.x % cv, ty = threadIdx.x / cv;
+  const unsigned ry = (unsigned)prm.ry;
+  const int c0 = (int)tx * 4;
+  double ai[4] = {0, 0, 0, 0}, ap[4] = {0, 0, 0, 0};
+  if (ty < ry) {
+    const unsigned rstride = gridDim.x * ry;
+    for (int s = 0; s < segs.num; ++s) {
+      const unsigned rows = (unsigned)segs.rows[s];
+      const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
+      const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
+      for (unsigned r0 = blockIdx.x * ry + ty; r0 < rows; r0 += UNROLL * rstride) {
+        float4 v[UNROLL];
+        int lab[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+          const unsigned r = r0 + j * rstride;
+          lab[j] = RN_LABEL_IGNORE;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < rows) {
+            v[j] = __ldcs(xin + (size_t)r * cv + tx);
+            lab[j] = __ldg(lab_p + r);
+          }
+        }
+        float fp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < UNROLL; ++j) {
+          if (lab[j] == RN_LABEL_IGNORE) continue;
+          const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float p;
+            if (xs[k] <= -0.70f) {
+              const float e = ex2_approx(xs[k] * 1.44269502163e+00f);
+              p = e * rcp_approx(1.0f + e);
+            } else {
+              p = sigmoid_f32(xs[k]);
+            }
+            fp[k] += p;
+            if (lab[j] == c0 + k) ai[k] += (double)p;   // at most one class per row
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ap[k] += (double)fp[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s_acc[(size_t)ty * 2 * C + c0 + k] = ai[k];
+      s_acc[(size_t)ty * 2 * C + C + c0 + k] = ap[k];
+    }
+  }
+  __syncthreads();
+  double* mine = prm.partials + (size_t)blockIdx.x * 2 * C;
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    double v = 0.0;
+    for (unsigned y = 0; y < ry; ++y) v += s_acc[(size_t)y * 2 * C + j];
+    mine[j] = v;
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (s_last) {
     __threadfence();
@@ -777,7 +976,6 @@ __global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float*
 
 // rn_set_option("fast_focal", 0) forces the generic kernel (used by the parity tests to cover both)
 static int g_fast_focal = 1;
-static int g_focal_minb = 4;  // resident CTAs per SM the fast focal kernel is compiled for (4 or 5)
 
 // Persistent grid: exactly the number of CTAs that are resident at once (one full wave), so a
 // grid-stride loop never runs a partially filled second wave.
@@ -794,7 +992,7 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem, long long wo
   return (unsigned)blocks;
 }
 
-static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, bool select, long long units,
+static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st);
 
 static unsigned loss_grid(long long units, int threads, int per_sm) {
@@ -829,21 +1027,43 @@ static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaS
     launch_cls<MODE, DICE, false>(vec4, grid, smem, st, segs, prm);
 }
 
-static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, bool select, long long units,
+template <int MODE, bool DICE>
+static void launch_fast_variant(const Segs& segs, const FocalFastParams& fp, bool select, long long work,
+                                size_t smem, cudaStream_t st) {
+#define RN_LAUNCH_FF(MINB, SEL)                                                                          \
+  do {                                                                                                   \
+    const unsigned g = persistent_grid(cls_fast_kernel<MODE, DICE, MINB, SEL>, kLossThreads, smem, work); \
+    cls_fast_kernel<MODE, DICE, MINB, SEL><<<g, kLossThreads, smem, st>>>(segs, fp);                     \
+  } while (0)
+  // 4 resident CTAs of 256 threads per SM (64 registers): measured faster than 5 x 48 registers
+  if (select) RN_LAUNCH_FF(4, true); else RN_LAUNCH_FF(4, false);
+#undef RN_LAUNCH_FF
+}
+
+static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st) {
   const long long work = (units + 1) / 2;
-#define RN_LAUNCH_FF(MINB, SEL)                                                                     \
-  do {                                                                                              \
-    const unsigned g = persistent_grid(cls_focal_fast_kernel<MINB, SEL>, kLossThreads, 0, work);    \
-    cls_focal_fast_kernel<MINB, SEL><<<g, kLossThreads, 0, st>>>(segs, fp);                         \
-  } while (0)
-  if (g_focal_minb >= 5) {
-    if (select) RN_LAUNCH_FF(5, true); else RN_LAUNCH_FF(5, false);
-  } else {
-    if (select) RN_LAUNCH_FF(4, true); else RN_LAUNCH_FF(4, false);
+  const int base = mode & 15;
+  const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
+  const size_t smem = (dice || base == RN_CLS_BALANCED_BCE) ? 4 * (size_t)fp.num_classes * sizeof(float) : 0;
+  switch (base) {
+    case RN_CLS_FOCAL:
+      if (dice) launch_fast_variant<RN_CLS_FOCAL, true>(segs, fp, select, work, smem, st);
+      else launch_fast_variant<RN_CLS_FOCAL, false>(segs, fp, select, work, smem, st);
+      break;
+    case RN_CLS_BCE:
+      if (dice) launch_fast_variant<RN_CLS_BCE, true>(segs, fp, select, work, smem, st);
+      else launch_fast_variant<RN_CLS_BCE, false>(segs, fp, select, work, smem, st);
+      break;
+    case RN_CLS_BALANCED_BCE:
+      if (dice) launch_fast_variant<RN_CLS_BALANCED_BCE, true>(segs, fp, select, work, smem, st);
+      else launch_fast_variant<RN_CLS_BALANCED_BCE, false>(segs, fp, select, work, smem, st);
+      break;
+    default:
+      launch_fast_variant<RN_CLS_NONE, true>(segs, fp, select, work, smem, st);
+      break;
   }
-#undef RN_LAUNCH_FF
-  RN_CUDA_CHECK_LAUNCH("focal fast kernel");
+  RN_CUDA_CHECK_LAUNCH("fast classification-loss kernel");
   return RN_OK;
 }
 
@@ -855,10 +1075,6 @@ extern "C" int rn_set_option(const char* name, int value) {
   RN_REQUIRE(name, RN_ERR_BAD_ARG, "rn_set_option: NULL name");
   if (strcmp(name, "fast_focal") == 0) {
     g_fast_focal = value != 0;
-    return RN_OK;
-  }
-  if (strcmp(name, "focal_min_blocks") == 0) {
-    g_focal_minb = value;
     return RN_OK;
   }
   rn::set_error("rn_set_option: unknown option '%s'", name);
@@ -906,6 +1122,26 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   RN_REQUIRE(smem <= 200 * 1024, RN_ERR_UNSUPPORTED, "rn_cls_sums: too many classes for shared memory");
   const long long total_rows = segs.start[RN_MAX_LEVELS];
   cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
+  bool rows32 = true;
+  for (int i = 0; i < rows->num_segments; ++i)
+    if (rows->rows[i] >= (1ll << 31) - (1ll << 26)) rows32 = false;
+  if (!dense_labels && vec4 && g_fast_focal && rows32 && prm.cv <= 256) {
+    prm.ry = 256 / prm.cv > 0 ? 256 / prm.cv : 1;
+    const int fthreads = prm.cv * prm.ry;
+    const size_t fsmem = (size_t)prm.ry * 2 * num_classes * sizeof(double);
+    if (fsmem <= 48 * 1024) {
+      int per_sm = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cls_sums_fast_kernel<4>, fthreads, fsmem);
+      long long fgrid = (long long)num_sms() * (per_sm > 0 ? per_sm : 1);
+      const long long need = (total_rows + prm.ry - 1) / prm.ry;
+      if (fgrid > need) fgrid = need;
+      if (fgrid > kMaxLossBlocks) fgrid = kMaxLossBlocks;
+      if (fgrid < 1) fgrid = 1;
+      cls_sums_fast_kernel<4><<<(unsigned)fgrid, fthreads, fsmem, st>>>(segs, prm);
+      RN_CUDA_CHECK_LAUNCH("rn_cls_sums(fast)");
+      return RN_OK;
+    }
+  }
   unsigned grid = loss_grid((total_rows + prm.ry - 1) / prm.ry, 1, 4);
 #define RN_LAUNCH_SUMS(DENSE, VEC)                                                                             \
   do {                                                                                                         \
@@ -969,7 +1205,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   bool fits32 = true;  // the fast kernel indexes float4 units with 32-bit integers
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
-  if (base == RN_CLS_FOCAL && !dice && !dense && vec4 && focus == 2.0f && g_fast_focal && fits32) {
+  if ((base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_focal && fits32 && num_classes <= 2048) {
     FocalFastParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.logits = prm.logits;
@@ -984,7 +1220,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     fp.num_classes = num_classes;
     fp.cv = num_classes / 4;
     fp.write_grad = prm.write_grad;
-    return launch_focal_fast(segs, fp, false, units, st);
+    return launch_focal_fast(segs, fp, mode, false, units, st);
   }
   switch (base) {
     case RN_CLS_FOCAL:
@@ -1008,8 +1244,9 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
 }
 
 extern "C" int rn_fused_select_supported(int num_classes, int mode, float focus, const rn_rows_t* rows) {
-  if (!rows || num_classes % 4 != 0 || (mode & 15) != RN_CLS_FOCAL || (mode & RN_CLS_DICE_FLAG) || focus != 2.0f ||
-      !g_fast_focal)
+  const int base = mode & 15;
+  if (!rows || num_classes % 4 != 0 || num_classes > 2048 || (base == RN_CLS_FOCAL && focus != 2.0f) ||
+      (base == RN_CLS_NONE && !(mode & RN_CLS_DICE_FLAG)) || !g_fast_focal)
     return 0;
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4) + (1ull << 24) >= (1ull << 32)) return 0;
@@ -1028,7 +1265,7 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
                  d_cand_count,
              RN_ERR_BAD_ARG, "rn_cls_loss_select: NULL input");
   RN_REQUIRE(rn_fused_select_supported(num_classes, mode, focus, rows), RN_ERR_UNSUPPORTED,
-             "rn_cls_loss_select: needs focal (focus 2), compact labels, C %% 4 == 0 and < 2^32 float4 per level; "
+             "rn_cls_loss_select: needs focus == 2 (focal), C %% 4 == 0 and < 2^32 float4 per level; "
              "use rn_cls_loss_fwd_bwd + rn_decode_select");
   RN_REQUIRE(rows->images >= 1 && capacity >= 1, RN_ERR_BAD_ARG, "rn_cls_loss_select: bad images/capacity");
   RN_REQUIRE(score_thr > 0.f && score_thr < 1.f, RN_ERR_BAD_ARG, "rn_cls_loss_select: score_thr must be in (0, 1)");
@@ -1074,7 +1311,7 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
   cudaMemsetAsync(fp.ticket, 0, sizeof(unsigned), st);
   cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * rows->images, st);
   const long long units = segs.start[RN_MAX_LEVELS] * (long long)fp.cv;
-  return launch_focal_fast(segs, fp, true, units, st);
+  return launch_focal_fast(segs, fp, mode, true, units, st);
 }
 
 extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const rn_maps_t* target,

@@ -201,8 +201,9 @@ class DenseHeadPath(object):
         else:
             m_dlogits, m_dreg = _lib.Maps(), _lib.Maps()
         if self.mode & _lib.RN_CLS_DICE_FLAG:
-            _lib.call('rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
-                      _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st)
+            self._stage('cls_sums', lambda: _lib.call(
+                'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
+                _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
             self._allreduce(self.stats[_lib.RN_STATS_HEADER + Cn:])
         self._stage('cls_loss', lambda: _lib.call(
             'rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, self.mode,
@@ -241,6 +242,11 @@ class DenseHeadPath(object):
             m_dreg = self._merged_maps(self.dreg, 16)
         else:
             m_dlogits, m_dreg = _lib.Maps(), _lib.Maps()
+        if self.mode & _lib.RN_CLS_DICE_FLAG:
+            self._stage('cls_sums', lambda: _lib.call(
+                'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
+                _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
+            self._allreduce(self.stats[_lib.RN_STATS_HEADER + Cn:])
         self._stage('cls_loss', lambda: _lib.call(
             'rn_cls_loss_select', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode,
             self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
