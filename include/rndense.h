@@ -82,6 +82,7 @@ typedef struct rn_level {
   int64_t anchor_offset;     /* anchors of earlier levels within ONE image                  */
   float y0, y_step;          /* centre_y(i) = y0 + y_step * i  (tf.linspace, dataset.py:19) */
   float x0, x_step;
+  float max_half_h, max_half_w; /* max over anchors of size / 2 (patch bounds of the assign kernel) */
   float anchor_h[RN_MAX_ANCHORS]; /* normalised sizes, float32                              */
   float anchor_w[RN_MAX_ANCHORS];
 } rn_level_t;

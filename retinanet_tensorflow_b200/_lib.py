@@ -35,6 +35,7 @@ class Level(C.Structure):
         ('tiles_x', C.c_int32), ('tiles_y', C.c_int32), ('tile_start', C.c_int32),
         ('anchor_offset', C.c_int64),
         ('y0', C.c_float), ('y_step', C.c_float), ('x0', C.c_float), ('x_step', C.c_float),
+        ('max_half_h', C.c_float), ('max_half_w', C.c_float),
         ('anchor_h', C.c_float * RN_MAX_ANCHORS), ('anchor_w', C.c_float * RN_MAX_ANCHORS),
     ]
 

@@ -51,6 +51,12 @@ static int finish_pyramid(rn_pyramid_t* p) {
     RN_REQUIRE(L.grid_h > 0 && L.grid_w > 0, RN_ERR_BAD_SHAPE, "level %d has an empty grid", l);
     fill_axis(L.grid_h, &L.y0, &L.y_step);
     fill_axis(L.grid_w, &L.x0, &L.x_step);
+    L.max_half_h = 0.f;
+    L.max_half_w = 0.f;
+    for (int a = 0; a < L.num_anchors; ++a) {
+      L.max_half_h = L.anchor_h[a] * 0.5f > L.max_half_h ? L.anchor_h[a] * 0.5f : L.max_half_h;
+      L.max_half_w = L.anchor_w[a] * 0.5f > L.max_half_w ? L.anchor_w[a] * 0.5f : L.max_half_w;
+    }
     L.tiles_x = (L.grid_w + kTileW - 1) / kTileW;
     L.tiles_y = (L.grid_h + kTileH - 1) / kTileH;
     L.tile_start = tiles;

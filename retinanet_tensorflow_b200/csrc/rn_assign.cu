@@ -33,15 +33,16 @@ __global__ void __launch_bounds__(kTileH * kTileW * 6)
 assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ AssignParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_box = reinterpret_cast<float4*>(smem_raw);                       // [max_gt] recomputed corners
-  float* s_area = reinterpret_cast<float*>(s_box + prm.max_gt);              // [max_gt]
+  float4* s_ctr = s_box + prm.max_gt;                                        // [max_gt] (cy, cx, h, w) of the raw box
+  float* s_area = reinterpret_cast<float*>(s_ctr + prm.max_gt);              // [max_gt]
   int* s_idx = reinterpret_cast<int*>(s_area + prm.max_gt);                  // [max_gt] original index
+  int* s_cls = s_idx + prm.max_gt;                                           // [max_gt] class id
   __shared__ int s_warp_cnt[32];
-  __shared__ int s_n;
-  __shared__ unsigned s_flags;
+  __shared__ float4 s_ctr0;   // GT 0 (the match of anchors that overlap nothing, dataset.py:76)
+  __shared__ int s_cls0;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int nwarps = (blockDim.x + 31) >> 5;
   const int b = blockIdx.x / pyr.tiles_per_image;
   const int tile = blockIdx.x - b * pyr.tiles_per_image;
   int l = 0;
@@ -53,60 +54,64 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
   const int ty1 = min(ty0 + kTileH, L.grid_h) - 1;  // inclusive
   const int tx1 = min(tx0 + kTileW, L.grid_w) - 1;
 
-  if (tid == 0) {
-    s_n = 0;
-    s_flags = 0;
-  }
-
   // ---- patch bounding box: fsub/fadd are monotone, so the extremes come from the corner cells
-  float max_hh = 0.f, max_hw = 0.f;
-  for (int a = 0; a < L.num_anchors; ++a) {
-    max_hh = fmaxf(max_hh, L.anchor_h[a] * 0.5f);
-    max_hw = fmaxf(max_hw, L.anchor_w[a] * 0.5f);
-  }
-  const float T0 = fsub(cell_centre(L.y0, L.y_step, ty0), max_hh);
-  const float T1 = fsub(cell_centre(L.x0, L.x_step, tx0), max_hw);
-  const float T2 = fadd(cell_centre(L.y0, L.y_step, ty1), max_hh);
-  const float T3 = fadd(cell_centre(L.x0, L.x_step, tx1), max_hw);
+  // and the level's largest half sizes (precomputed on the host)
+  const float T0 = fsub(cell_centre(L.y0, L.y_step, ty0), L.max_half_h);
+  const float T1 = fsub(cell_centre(L.x0, L.x_step, tx0), L.max_half_w);
+  const float T2 = fadd(cell_centre(L.y0, L.y_step, ty1), L.max_half_h);
+  const float T3 = fadd(cell_centre(L.x0, L.x_step, tx1), L.max_half_w);
 
-  // ---- stage the GT boxes that touch the patch, in original order
-  const int n_gt = min(max(prm.gt_counts[b], 0), prm.max_gt);
+  // ---- stage the GT boxes that touch the patch, in original order.  The count and the boxes
+  // are loaded together (padding rows are simply masked afterwards).
   const float4* gt = prm.gt_boxes + (size_t)b * prm.max_gt;
+  const int32_t* gcls = prm.gt_classes + (size_t)b * prm.max_gt;
+  const int n_gt = min(max(__ldg(prm.gt_counts + b), 0), prm.max_gt);
   unsigned flags = 0;
-  __syncthreads();
-  for (int base = 0; base < n_gt; base += blockDim.x) {
+  int n_kept = 0;
+  // (the first chunk is processed unconditionally so that its loads do not wait for the count)
+  for (int base = 0; base < prm.max_gt && (base == 0 || base < n_gt); base += blockDim.x) {
     const int i = base + tid;
     bool keep = false;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n_gt) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), ctr = g;
+    int cls = -1;
+    if (i < prm.max_gt) {
       const float4 raw = __ldg(gt + i);
+      cls = __ldg(gcls + i);
       // to_center_box (dataset.py:28-32) then from_center_box (dataset.py:35-39)
       const float sh = fsub(raw.z, raw.x), sw = fsub(raw.w, raw.y);
       const float cy = fadd(raw.x, sh * 0.5f), cx = fadd(raw.y, sw * 0.5f);
+      ctr = make_float4(cy, cx, sh, sw);
       g = make_float4(fsub(cy, sh * 0.5f), fsub(cx, sw * 0.5f), fadd(cy, sh * 0.5f), fadd(cx, sw * 0.5f));
-      if (!(g.x <= g.z && g.y <= g.w)) flags |= RN_FLAG_BOX_ORDER;  // utils.py:67
-      keep = !(g.z < T0 || g.x > T2 || g.w < T1 || g.y > T3);
+      if (i < n_gt) {
+        if (!(g.x <= g.z && g.y <= g.w)) flags |= RN_FLAG_BOX_ORDER;  // utils.py:67
+        keep = !(g.z < T0 || g.x > T2 || g.w < T1 || g.y > T3);
+        if (i == 0) {
+          s_ctr0 = ctr;
+          s_cls0 = cls;
+        }
+      }
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_warp_cnt[warp] = __popc(m);
     __syncthreads();
-    int off = s_n;
-    for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
+    int off = n_kept, tot = 0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) {
+      const int c = s_warp_cnt[w];
+      off += w < warp ? c : 0;
+      tot += c;
+    }
     if (keep) {
       const int pos = off + __popc(m & ((1u << lane) - 1u));
       s_box[pos] = g;
+      s_ctr[pos] = ctr;
       s_area[pos] = fmul(fsub(g.z, g.x), fsub(g.w, g.y));  // box_b_area (utils.py:84-85)
       s_idx[pos] = i;
+      s_cls[pos] = cls;
     }
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < nwarps; ++w) tot += s_warp_cnt[w];
-      s_n += tot;
-    }
+    n_kept += tot;
     __syncthreads();
   }
-  const int n_kept = s_n;
 
   // ---- this thread's anchors
   const int cell_local = tid / prm.tpc;
@@ -134,7 +139,9 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
     bestj[k] = -1;
   }
 
-  // ---- IoU scan (utils.iou, utils.py:70-92), strict '>' keeps the first maximum
+  // ---- IoU scan (utils.iou, utils.py:70-92), strict '>' keeps the first maximum.  The IEEE
+  // division only runs when the pair can beat the running best: rcp.approx bounds the quotient
+  // to 4e-7 relative, so `approx * (1 + 2e-6) <= best` proves fl(inter / uni) <= best.
   for (int j = 0; j < n_kept; ++j) {
     const float4 g = s_box[j];
     const float ga = s_area[j];
@@ -145,62 +152,71 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
       if (!(yb < yt || xr < xl)) {
         const float inter = fmul(fsub(yb, yt), fsub(xr, xl));
         const float uni = fsub(fadd(aa[k], ga), inter);
-        const float v = fdiv(inter, uni);
-        if (!(v >= 0.f && v <= 1.f)) flags |= RN_FLAG_IOU_RANGE;  // utils.py:94
-        if (v > best[k]) {
-          best[k] = v;
-          bestj[k] = j;
+        const float approx = inter * rcp_approx(uni);
+        if (!(approx >= 0.f && approx <= 1.001f)) flags |= RN_FLAG_IOU_RANGE;  // utils.py:94 (NaN, < 0, > 1)
+        if (approx * 1.000002f > best[k]) {
+          const float v = fdiv(inter, uni);
+          if (!(v <= 1.f)) flags |= RN_FLAG_IOU_RANGE;
+          if (v > best[k]) {
+            best[k] = v;
+            bestj[k] = j;
+          }
         }
       }
     }
   }
 
   // ---- labels + encoding for the matched box (all anchors, dataset.py:105-121)
-  int n_train = 0, n_fg = 0;
+  int n_ign = 0, n_fg = 0;   // both rare: the common warp issues no atomic at all
   if (n_gt == 0 && tid == 0) flags |= RN_FLAG_EMPTY_GT;
+  const long long cell_row = ((long long)b * L.grid_h * L.grid_w + (long long)cy_i * L.grid_w + cx_i) * L.num_anchors;
 #pragma unroll
   for (int k = 0; k < kApt; ++k) {
     if (!ok[k]) continue;
     const int a = sub * kApt + k;
-    const long long row = ((long long)b * L.grid_h * L.grid_w + (long long)cy_i * L.grid_w + cx_i) * L.num_anchors + a;
-    const int gi = bestj[k] >= 0 ? s_idx[bestj[k]] : 0;
+    const long long row = cell_row + a;
     int lab = RN_LABEL_BACKGROUND;
     float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
     int matched = -1;
     if (n_gt > 0) {
-      matched = gi;
+      const bool hit = bestj[k] >= 0;
+      matched = hit ? s_idx[bestj[k]] : 0;
+      const float4 t = hit ? s_ctr[bestj[k]] : s_ctr0;   // (cy, cx, h, w) of the matched raw box
       const bool pos = best[k] >= prm.pos_thr;                 // !bg_mask, dataset.py:83
       const bool ign = !pos && !(best[k] < prm.neg_thr);       // !trainable_mask, dataset.py:87
       if (pos) {
-        const int c = __ldg(prm.gt_classes + (size_t)b * prm.max_gt + gi);
+        const int c = hit ? s_cls[bestj[k]] : s_cls0;
         lab = (c >= 0 && c < prm.num_classes) ? c : RN_LABEL_BACKGROUND;  // one_hot of an out-of-range id is 0
       } else if (ign) {
         lab = RN_LABEL_IGNORE;
       }
-      const float4 raw = __ldg(gt + gi);
-      const float th = fsub(raw.z, raw.x), tw = fsub(raw.w, raw.y);
-      const float tcy = fadd(raw.x, th * 0.5f), tcx = fadd(raw.y, tw * 0.5f);
       const float h = L.anchor_h[a], w = L.anchor_w[a];
-      d.x = fdiv(fsub(tcy, cy), h);   // shifts, dataset.py:108
-      d.y = fdiv(fsub(tcx, cx), w);
-      d.z = logf(fdiv(th, h));        // log(scales), dataset.py:110-112
-      d.w = logf(fdiv(tw, w));
+      d.x = fdiv(fsub(t.x, cy), h);   // shifts, dataset.py:108
+      d.y = fdiv(fsub(t.y, cx), w);
+      const float rh = fdiv(t.z, h), rw = fdiv(t.w, w);   // scales, dataset.py:110
+      d.z = rh > 0.f ? log_fast(rh) : logf(rh);           // log(scales), dataset.py:112
+      d.w = rw > 0.f ? log_fast(rw) : logf(rw);
     }
     reinterpret_cast<int32_t*>(prm.matched.p[l])[row] = matched;
     reinterpret_cast<int32_t*>(prm.label.p[l])[row] = lab;
     reinterpret_cast<float4*>(prm.deltas.p[l])[row] = d;
     if (prm.iou_max.p[0]) reinterpret_cast<float*>(prm.iou_max.p[l])[row] = best[k];
-    n_train += lab != RN_LABEL_IGNORE;
+    n_ign += lab == RN_LABEL_IGNORE;
     n_fg += lab >= 0;
     if (prm.stats && lab >= 0) atomicAdd(prm.stats + RN_STAT_NPOS(lab), 1.0);
   }
 
   if (prm.stats) {
-    n_train = warp_sum(n_train);
-    n_fg = warp_sum(n_fg);
-    if (lane == 0) {
-      if (n_train) atomicAdd(prm.stats + RN_STAT_TRAINABLE, (double)n_train);
-      if (n_fg) atomicAdd(prm.stats + RN_STAT_NUM_FG, (double)n_fg);
+    // M = all anchors - ignored: the constant part is added once, ignored anchors are rare
+    if (blockIdx.x == 0 && tid == 0)
+      atomicAdd(prm.stats + RN_STAT_TRAINABLE, (double)pyr.anchors_per_image * (double)(gridDim.x / pyr.tiles_per_image));
+    if (__any_sync(0xffffffffu, (n_ign | n_fg) != 0)) {
+      n_ign = warp_sum(n_ign);
+      n_fg = warp_sum(n_fg);
+      if (lane == 0) {
+        if (n_ign) atomicAdd(prm.stats + RN_STAT_TRAINABLE, -(double)n_ign);
+        if (n_fg) atomicAdd(prm.stats + RN_STAT_NUM_FG, (double)n_fg);
+      }
     }
   }
   if (prm.status) {
@@ -291,23 +307,24 @@ __global__ void iou_pairwise_kernel(long long n, const float4* __restrict__ a, c
 __global__ void label_stats_kernel(const __grid_constant__ Segs segs, int num_classes,
                                    const __grid_constant__ Ptrs label, double* stats) {
   const long long total = segs.start[RN_MAX_LEVELS];
-  int n_train = 0, n_fg = 0;
+  int n_ign = 0, n_fg = 0;
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total;
        r += (long long)gridDim.x * blockDim.x) {
     const int s = seg_of(segs, r);
     const int lab = reinterpret_cast<const int32_t*>(label.p[s])[r - segs.start[s]];
-    n_train += lab != RN_LABEL_IGNORE;
+    n_ign += lab == RN_LABEL_IGNORE;
     if (lab >= 0 && lab < num_classes) {
       n_fg += 1;
       atomicAdd(stats + RN_STAT_NPOS(lab), 1.0);
     }
   }
-  n_train = warp_sum(n_train);
+  n_ign = warp_sum(n_ign);
   n_fg = warp_sum(n_fg);
   if ((threadIdx.x & 31) == 0) {
-    if (n_train) atomicAdd(stats + RN_STAT_TRAINABLE, (double)n_train);
+    if (n_ign) atomicAdd(stats + RN_STAT_TRAINABLE, -(double)n_ign);
     if (n_fg) atomicAdd(stats + RN_STAT_NUM_FG, (double)n_fg);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + RN_STAT_TRAINABLE, (double)total);
 }
 
 static unsigned grid_for(long long work_items, int threads, int per_sm = 8) {
@@ -357,7 +374,7 @@ extern "C" int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float*
   prm.status = d_status;
   prm.tpc = (na + kApt - 1) / kApt;
   const int threads = kTileH * kTileW * prm.tpc;
-  const size_t smem = (size_t)max_gt * (sizeof(float4) + sizeof(float) + sizeof(int));
+  const size_t smem = (size_t)max_gt * (2 * sizeof(float4) + sizeof(float) + 2 * sizeof(int));
   const long long blocks = (long long)batch * pyr->tiles_per_image;
   RN_REQUIRE(blocks < (1ll << 31), RN_ERR_BAD_SHAPE, "too many tiles");
   assign_encode_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(*pyr, prm);

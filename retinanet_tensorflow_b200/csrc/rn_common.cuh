@@ -82,6 +82,40 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 // tf.nn.sigmoid as the oracle states it: 1 / (1 + exp(-x)), every op rounded to float32.
 __device__ __forceinline__ float sigmoid_f32(float x) { return fdiv(1.0f, fadd(1.0f, expf(-x))); }
 
+// ---- cheap ~1 ulp primitives shared by the fast kernels ---------------------------------------
+__device__ __forceinline__ float ex2_approx(float t) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return r;
+}
+__device__ __forceinline__ float rcp_newton(float d) {
+  const float r = rcp_approx(d);
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
+}
+// log(a) for positive normal a (any positive normal float); no I2F (XU pipe): the
+// exponent becomes a float through the 1.5*2^23 magic constant.
+__device__ __forceinline__ float log_fast(float a) {
+  const int ia = __float_as_int(a);
+  const int e = (ia - 0x3f2aaaab) & 0xff800000;
+  const float f = __int_as_float(ia - e) - 1.0f;  // mantissa in [2/3, 4/3] minus 1
+  const float kf = __int_as_float((e >> 23) + 0x4b400000) - 12582912.0f;
+  float q = 1.402632743e-01f;
+  q = fmaf(q, f, -1.538854539e-01f);
+  q = fmaf(q, f, 1.399581283e-01f);
+  q = fmaf(q, f, -1.641595960e-01f);
+  q = fmaf(q, f, 2.001116872e-01f);
+  q = fmaf(q, f, -2.500782013e-01f);
+  q = fmaf(q, f, 3.333319724e-01f);
+  q = fmaf(q, f, -4.999993742e-01f);
+  const float r = fmaf(f * f, q, f);
+  return fmaf(kf, 0.693147182f, r);
+}
+
 // ---- streaming loads / stores ----------------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
   return __ldcs(reinterpret_cast<const float4*>(p));

@@ -219,20 +219,6 @@ cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsPa
 // and treats every element as a negative (z = 0); the at-most-one positive element of a row is
 // recomputed afterwards on a rare path.  Row/column of a unit advance incrementally, so the
 // loop has no division.
-__device__ __forceinline__ float ex2_approx(float t) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
-  return r;
-}
-__device__ __forceinline__ float rcp_approx(float d) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  return r;
-}
-__device__ __forceinline__ float rcp_newton(float d) {
-  const float r = rcp_approx(d);
-  return fmaf(r, fmaf(-d, r, 1.0f), r);
-}
 // exp(-x), clamped so that 1 + e stays finite.  The product x*log2(e) is split into its rounded
 // value and its exact rounding error (one FFMA), so the result carries only ex2.approx's error.
 __device__ __forceinline__ float exp_neg_fast(float x) {
@@ -242,25 +228,6 @@ __device__ __forceinline__ float exp_neg_fast(float x) {
   const float e = ex2_approx(fminf(t, 126.0f));
   return fmaf(e * r, 0.693147182f, e);
 }
-// log(a) for positive normal a (here a = p_t + eps in [1e-7, 1 + 1e-7]); no I2F (XU pipe): the
-// exponent becomes a float through the 1.5*2^23 magic constant.
-__device__ __forceinline__ float log_fast(float a) {
-  const int ia = __float_as_int(a);
-  const int e = (ia - 0x3f2aaaab) & 0xff800000;
-  const float f = __int_as_float(ia - e) - 1.0f;  // mantissa in [2/3, 4/3] minus 1
-  const float kf = __int_as_float((e >> 23) + 0x4b400000) - 12582912.0f;
-  float q = 1.402632743e-01f;
-  q = fmaf(q, f, -1.538854539e-01f);
-  q = fmaf(q, f, 1.399581283e-01f);
-  q = fmaf(q, f, -1.641595960e-01f);
-  q = fmaf(q, f, 2.001116872e-01f);
-  q = fmaf(q, f, -2.500782013e-01f);
-  q = fmaf(q, f, 3.333319724e-01f);
-  q = fmaf(q, f, -4.999993742e-01f);
-  const float r = fmaf(f * f, q, f);
-  return fmaf(kf, 0.693147182f, r);
-}
-
 struct FocalFastParams {
   Ptrs logits, label, dlogits;
   float alpha, eps;
