@@ -308,23 +308,180 @@ __device__ __forceinline__ float bce_neg_bulk(float x, float& p) {
   return fmaf(e * e, t, e);
 }
 
+// Per-thread state of the fast kernel that both the hot loop and the rare path need.
+struct FastCtx {
+  const float* s_tab;   // [4][C] w_neg, w_pos, dice A, dice B (shared memory)
+  int C;
+  float eps, cg, inv_fg, inv_mc, alpha;
+};
+
+// ---- rare path (noinline keeps it out of the hot loop's register allocation) -----------------------
+// Handles one float4 unit that is not "four confident negatives": hard negatives, the row's positive
+// element, and -- when SELECT -- the candidate pre-selection.  Returns the four loss partials in l
+// (focal: w^2 log(.) terms of negatives; the positive's full loss goes to acc_pos).
+struct UnitOut {
+  float4 g, l;
+  float pos;   // focal: the positive element's own loss (summed separately, it has no -(1-alpha) factor)
+};
+
+template <int MODE, bool DICE, bool SELECT>
+__device__ __noinline__ UnitOut fast_slow_unit(FastCtx cx, const FocalFastParams& prm, const Segs& segs, int s,
+                                               unsigned row, unsigned c4, int lab, float4 v) {
+  UnitOut out;
+  out.pos = 0.f;
+  float4& g = out.g;
+  float4& l = out.l;
+  const float xs[4] = {v.x, v.y, v.z, v.w};
+  if (SELECT) {
+    float bp = -INFINITY;
+    int bc = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (xs[k] > prm.sel_trigger) {
+        const float pk = sigmoid_f32(xs[k]);
+        if (pk > bp) {
+          bp = pk;
+          bc = (int)c4 + k;
+        }
+      }
+    }
+    if (bp > prm.sel_thr) {
+      const unsigned per_image = (unsigned)(segs.rows[s] / prm.sel_images);
+      const unsigned bimg = row / per_image;
+      const int anchor = (int)(segs.start[s] / prm.sel_images) + (int)(row - bimg * per_image);
+      const int slot = atomicAdd(prm.sel_count + bimg, 1);
+      if (slot < prm.sel_capacity) {
+        const size_t o = (size_t)bimg * prm.sel_capacity + slot;
+        prm.sel_anchor[o] = anchor;
+        prm.sel_score[o] = bp;
+        prm.sel_class[o] = bc;
+      } else if (prm.status) {
+        atomicOr(prm.status, RN_FLAG_CAND_OVERFLOW);
+      }
+    }
+  }
+  g = make_float4(0.f, 0.f, 0.f, 0.f);
+  l = g;
+  if (lab == RN_LABEL_IGNORE) return out;
+  const unsigned d = (unsigned)(lab - (int)c4);
+  const float* s_wneg = cx.s_tab;
+  const float* s_wpos = cx.s_tab + cx.C;
+  const float* s_da = cx.s_tab + 2 * cx.C;
+  const float* s_db = cx.s_tab + 3 * cx.C;
+  float ls[4], gs[4];
+  if constexpr (MODE == RN_CLS_FOCAL) {
+    LossScalars sc;
+    sc.focus = 2.0f;
+    sc.alpha = cx.alpha;
+    sc.one_minus_alpha = 1.0f - cx.alpha;
+    sc.eps = cx.eps;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float pq;
+      ls[k] = focal_neg_fast(xs[k], cx.eps, cx.cg, gs[k], pq);
+      if (d == (unsigned)k) {  // the row's positive class: redo this element with z = 1
+        float lp, gp;
+        focal_elem<true>(xs[k], true, sc, lp, gp);
+        gp *= cx.inv_fg;
+        out.pos += lp;
+        if (DICE) gp += s_da[c4 + k] * pq;
+        ls[k] = 0.f;
+        gs[k] = gp;
+      }
+      if (DICE) gs[k] = fmaf(s_db[c4 + k], pq, gs[k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float z = (d == (unsigned)k) ? 1.0f : 0.0f;
+      float loss = 0.f, pk = 0.f, dx = 0.f;
+      bce_elem<true>(xs[k], z, loss, pk, dx);
+      float gk = 0.f;
+      if (MODE == RN_CLS_NONE) {
+        loss = 0.f;
+      } else {
+        float wk = 1.0f;
+        if (MODE == RN_CLS_BALANCED_BCE) wk = z == 1.0f ? s_wpos[c4 + k] : s_wneg[c4 + k];
+        loss *= wk;
+        gk = dx * (cx.inv_mc * wk);
+      }
+      if (DICE) gk += (z * s_da[c4 + k] + s_db[c4 + k]) * (pk * (1.0f - pk));
+      ls[k] = loss;
+      gs[k] = gk;
+    }
+  }
+  l = make_float4(ls[0], ls[1], ls[2], ls[3]);
+  g = make_float4(gs[0], gs[1], gs[2], gs[3]);
+  return out;
+}
+
+// ---- hot path: four confident negatives (every logit <= -0.70, no positive in the unit) --------------
+template <int MODE, bool DICE>
+__device__ __forceinline__ void fast_bulk_unit(const FastCtx cx, unsigned c4, float4 v, float4& g, float4& l) {
+  if constexpr (MODE == RN_CLS_FOCAL) {
+    float pq0, pq1, pq2, pq3;
+    l.x = focal_neg_bulk(v.x, cx.eps, cx.cg, g.x, pq0);
+    l.y = focal_neg_bulk(v.y, cx.eps, cx.cg, g.y, pq1);
+    l.z = focal_neg_bulk(v.z, cx.eps, cx.cg, g.z, pq2);
+    l.w = focal_neg_bulk(v.w, cx.eps, cx.cg, g.w, pq3);
+    if (DICE) {
+      const float4 db = *reinterpret_cast<const float4*>(cx.s_tab + 3 * cx.C + c4);
+      g.x = fmaf(db.x, pq0, g.x);
+      g.y = fmaf(db.y, pq1, g.y);
+      g.z = fmaf(db.z, pq2, g.z);
+      g.w = fmaf(db.w, pq3, g.w);
+    }
+  } else {
+    float4 wn = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MODE == RN_CLS_BALANCED_BCE) wn = *reinterpret_cast<const float4*>(cx.s_tab + c4);
+    float p0, p1, p2, p3;
+    l.x = bce_neg_bulk(v.x, p0);
+    l.y = bce_neg_bulk(v.y, p1);
+    l.z = bce_neg_bulk(v.z, p2);
+    l.w = bce_neg_bulk(v.w, p3);
+    if (MODE == RN_CLS_NONE) {
+      l = make_float4(0.f, 0.f, 0.f, 0.f);
+      g = l;
+    } else {
+      g.x = p0 * (cx.inv_mc * wn.x);
+      g.y = p1 * (cx.inv_mc * wn.y);
+      g.z = p2 * (cx.inv_mc * wn.z);
+      g.w = p3 * (cx.inv_mc * wn.w);
+      if (MODE == RN_CLS_BALANCED_BCE) {
+        l.x *= wn.x; l.y *= wn.y; l.z *= wn.z; l.w *= wn.w;
+      }
+    }
+    if (DICE) {
+      const float4 db = *reinterpret_cast<const float4*>(cx.s_tab + 3 * cx.C + c4);
+      g.x = fmaf(db.x, p0 * (1.0f - p0), g.x);
+      g.y = fmaf(db.y, p1 * (1.0f - p1), g.y);
+      g.z = fmaf(db.z, p2 * (1.0f - p2), g.z);
+      g.w = fmaf(db.w, p3 * (1.0f - p3), g.w);
+    }
+  }
+}
+
 // MODE: RN_CLS_FOCAL (focus 2) | RN_CLS_BCE | RN_CLS_BALANCED_BCE | RN_CLS_NONE; DICE adds the dice
 // gradient (z A_c + B_c) p (1-p).  Compact labels, C % 4 == 0.
-template <int MODE, bool DICE, int MINB, bool SELECT>
+// FIXED_COL: the grid stride is a multiple of the row length, so a thread's float4 column never
+// changes and its row advances by a constant (no wrap test in the loop).
+template <int MODE, bool DICE, int MINB, bool SELECT, bool FIXED_COL>
 __global__ void __launch_bounds__(kLossThreads, MINB)
 cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
   extern __shared__ __align__(16) float s_tab[];   // [4][C]: w_neg, w_pos, dice A, dice B (when needed)
   __shared__ double s_red[32];
   constexpr bool kTables = DICE || MODE == RN_CLS_BALANCED_BCE;
   const int C = prm.num_classes;
-  const float* s_wneg = s_tab;
-  const float* s_wpos = s_tab + C;
-  const float* s_da = s_tab + 2 * C;
-  const float* s_db = s_tab + 3 * C;
   const double nfg = prm.stats[RN_STAT_NUM_FG];
   const double M = prm.stats[RN_STAT_TRAINABLE];
-  const float inv_fg = (float)(1.0 / fmax(nfg, 1.0));
-  const float inv_mc = M > 0 ? (float)(1.0 / (M * (double)C)) : 0.0f;
+  FastCtx cx;
+  cx.s_tab = s_tab;
+  cx.C = C;
+  cx.eps = prm.eps;
+  cx.alpha = prm.alpha;
+  cx.inv_fg = (float)(1.0 / fmax(nfg, 1.0));
+  cx.inv_mc = M > 0 ? (float)(1.0 / (M * (double)C)) : 0.0f;
+  cx.cg = (1.0f - prm.alpha) * cx.inv_fg;
   if (kTables) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const double npos = prm.stats[RN_STAT_NPOS(c)];
@@ -346,212 +503,89 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ Focal
     }
     __syncthreads();
   }
-  const float cg = (1.0f - prm.alpha) * inv_fg;
-  const float eps = prm.eps;
-  LossScalars sc;
-  sc.focus = 2.0f;
-  sc.alpha = prm.alpha;
-  sc.one_minus_alpha = 1.0f - prm.alpha;
-  sc.eps = prm.eps;
   const unsigned cv = (unsigned)prm.cv;
   const unsigned gstride = gridDim.x * blockDim.x;
-  const unsigned drow = gstride / cv, dcol = gstride % cv;
+  const unsigned drow = gstride / cv, dcol = gstride % cv;   // dcol == 0 when FIXED_COL
   const bool write_grad = prm.write_grad != 0;
-  double acc_neg = 0.0, acc_pos = 0.0;   // sum of w^2 log(.) over negatives; sum of positives' losses
+  const float trig = SELECT ? prm.sel_trigger : INFINITY;
+  double acc_neg = 0.0, acc_pos = 0.0;
 
   for (int s = 0; s < segs.num; ++s) {
-    const unsigned units = (unsigned)segs.rows[s] * cv;   // < 2^32, checked by the host
+    const unsigned units = (unsigned)segs.rows[s] * cv;   // < 2^32 - 2^24, checked by the host
     const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
     const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
     float4* __restrict__ gout = reinterpret_cast<float4*>(prm.dlogits.p[s]);
     unsigned u = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned row = u / cv;          // one division per thread per segment
     unsigned col = u - row * cv;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four short float accumulators
-    // Two units per iteration and a one-iteration register prefetch: the loads of iteration i+1
-    // are issued before the math of iteration i, so every thread keeps four 128-bit loads in
-    // flight (Little: ~35 KB per SM must be in flight to cover HBM latency at full bandwidth).
-    // u + 4*gstride cannot wrap: units + 2^24 < 2^32 is part of the host-side check
-    unsigned col1 = col + dcol, row1 = row + drow;
-    if (col1 >= cv) {
-      col1 -= cv;
-      row1 += 1;
+    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);   // four short float accumulators
+
+    // one unit: classify, compute, store
+    auto do_unit = [&](unsigned uu, unsigned rr, unsigned cc, const float4& v, int lab) {
+      const unsigned c4 = cc * 4u;
+      float4 g, l;
+      const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+      const bool plain = xmax <= -0.70f && (unsigned)(lab - (int)c4) >= 4u;   // also true for IGNORE (< 0)
+      if (plain && xmax <= trig) {
+        if (lab != RN_LABEL_IGNORE) {
+          fast_bulk_unit<MODE, DICE>(cx, c4, v, g, l);
+          acc4.x += l.x; acc4.y += l.y; acc4.z += l.z; acc4.w += l.w;
+        } else {
+          g = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        const UnitOut o = fast_slow_unit<MODE, DICE, SELECT>(cx, prm, segs, s, rr, c4, lab, v);
+        g = o.g;
+        acc4.x += o.l.x; acc4.y += o.l.y; acc4.z += o.l.z; acc4.w += o.l.w;
+        acc_pos += (double)o.pos;
+      }
+      if (write_grad) __stcs(gout + uu, g);
+    };
+
+    // main loop: four units per iteration, all loads first, no bounds tests
+    // (u + 4*gstride cannot wrap: units + 2^24 < 2^32 is part of the host-side check)
+    while (u + 3u * gstride < units) {
+      unsigned r1, r2, r3, c1, c2, c3;
+      if (FIXED_COL) {
+        r1 = row + drow; r2 = r1 + drow; r3 = r2 + drow;
+        c1 = c2 = c3 = col;
+      } else {
+        c1 = col + dcol; r1 = row + drow; if (c1 >= cv) { c1 -= cv; r1 += 1; }
+        c2 = c1 + dcol;  r2 = r1 + drow;  if (c2 >= cv) { c2 -= cv; r2 += 1; }
+        c3 = c2 + dcol;  r3 = r2 + drow;  if (c3 >= cv) { c3 -= cv; r3 += 1; }
+      }
+      const float4 v0 = __ldcs(xin + u);
+      const float4 v1 = __ldcs(xin + u + gstride);
+      const float4 v2 = __ldcs(xin + u + 2u * gstride);
+      const float4 v3 = __ldcs(xin + u + 3u * gstride);
+      const int l0 = __ldg(lab_p + row);
+      const int l1 = __ldg(lab_p + r1);
+      const int l2 = __ldg(lab_p + r2);
+      const int l3 = __ldg(lab_p + r3);
+      do_unit(u, row, col, v0, l0);
+      do_unit(u + gstride, r1, c1, v1, l1);
+      do_unit(u + 2u * gstride, r2, c2, v2, l2);
+      do_unit(u + 3u * gstride, r3, c3, v3, l3);
+      u += 4u * gstride;
+      if (FIXED_COL) {
+        row = r3 + drow;
+      } else {
+        col = c3 + dcol; row = r3 + drow; if (col >= cv) { col -= cv; row += 1; }
+      }
     }
-    float4 nv0 = make_float4(0.f, 0.f, 0.f, 0.f), nv1 = nv0;
-    int nlab0 = RN_LABEL_IGNORE, nlab1 = RN_LABEL_IGNORE;
-    if (u < units) {
-      nv0 = __ldcs(xin + u);
-      nlab0 = __ldg(lab_p + row);
-    }
-    if (u + gstride < units) {
-      nv1 = __ldcs(xin + u + gstride);
-      nlab1 = __ldg(lab_p + row1);
-    }
-    for (; u < units; u += 2 * gstride) {
-      const unsigned u1 = u + gstride;
-      const bool has1 = u1 < units;
-      const float4 v0 = nv0, v1 = nv1;
-      const int lab0 = nlab0, lab1 = nlab1;
-      const unsigned ccol = col, ccol1 = col1;
-      const unsigned srow = row, srow1 = row1;
-      (void)srow; (void)srow1;
-      // next iteration's coordinates and loads
-      col = col1 + dcol;
-      row = row1 + drow;
+    // tail: at most three units
+    for (; u < units; u += gstride) {
+      const float4 v = __ldcs(xin + u);
+      const int lab = __ldg(lab_p + row);
+      do_unit(u, row, col, v, lab);
+      col += dcol;
+      row += drow;
       if (col >= cv) {
         col -= cv;
         row += 1;
       }
-      col1 = col + dcol;
-      row1 = row + drow;
-      if (col1 >= cv) {
-        col1 -= cv;
-        row1 += 1;
-      }
-      const unsigned un = u + 2 * gstride;
-      nlab0 = RN_LABEL_IGNORE;
-      nlab1 = RN_LABEL_IGNORE;
-      if (un < units) {
-        nv0 = __ldcs(xin + un);
-        nlab0 = __ldg(lab_p + row);
-      }
-      if (un + gstride < units) {
-        nv1 = __ldcs(xin + un + gstride);
-        nlab1 = __ldg(lab_p + row1);
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const float4 v = half ? v1 : v0;
-        const int lab = half ? lab1 : lab0;
-        const unsigned c4 = (half ? ccol1 : ccol) * 4u;
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-        if (SELECT && xmax > prm.sel_trigger && (half == 0 || has1)) {
-          // rare: some class of this anchor may exceed the score threshold.  Evaluate the exact
-          // sigmoid for those elements and append the unit's best (max prob, first class).
-          const float xs[4] = {v.x, v.y, v.z, v.w};
-          float bp = -INFINITY;
-          int bc = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (xs[k] > prm.sel_trigger) {
-              const float pk = sigmoid_f32(xs[k]);
-              if (pk > bp) {
-                bp = pk;
-                bc = (int)c4 + k;
-              }
-            }
-          }
-          if (bp > prm.sel_thr) {
-            const unsigned r = half ? srow1 : srow;
-            const unsigned per_image = (unsigned)(segs.rows[s] / prm.sel_images);
-            const unsigned bimg = r / per_image;
-            const int anchor = (int)(segs.start[s] / prm.sel_images) + (int)(r - bimg * per_image);
-            const int slot = atomicAdd(prm.sel_count + bimg, 1);
-            if (slot < prm.sel_capacity) {
-              const size_t o = (size_t)bimg * prm.sel_capacity + slot;
-              prm.sel_anchor[o] = anchor;
-              prm.sel_score[o] = bp;
-              prm.sel_class[o] = bc;
-            } else if (prm.status) {
-              atomicOr(prm.status, RN_FLAG_CAND_OVERFLOW);
-            }
-          }
-        }
-        if (lab != RN_LABEL_IGNORE) {
-          float l0, l1, l2, l3;
-          const unsigned d = (unsigned)(lab - (int)c4);
-          const bool bulk = xmax <= -0.70f && d >= 4u;   // four confident negatives
-          if constexpr (MODE == RN_CLS_FOCAL) {
-            float pq0 = 0.f, pq1 = 0.f, pq2 = 0.f, pq3 = 0.f;
-            if (bulk) {
-              l0 = focal_neg_bulk(v.x, eps, cg, g.x, pq0);
-              l1 = focal_neg_bulk(v.y, eps, cg, g.y, pq1);
-              l2 = focal_neg_bulk(v.z, eps, cg, g.z, pq2);
-              l3 = focal_neg_bulk(v.w, eps, cg, g.w, pq3);
-            } else {
-              l0 = focal_neg_fast(v.x, eps, cg, g.x, pq0);
-              l1 = focal_neg_fast(v.y, eps, cg, g.y, pq1);
-              l2 = focal_neg_fast(v.z, eps, cg, g.z, pq2);
-              l3 = focal_neg_fast(v.w, eps, cg, g.w, pq3);
-              if (d < 4u) {  // the row's positive class sits in this unit: redo that element with z = 1
-                const float xv = d == 0 ? v.x : d == 1 ? v.y : d == 2 ? v.z : v.w;
-                float lp, gp;
-                focal_elem<true>(xv, true, sc, lp, gp);
-                gp *= inv_fg;
-                acc_pos += (double)lp;
-                if (DICE) gp += s_da[c4 + d] * (d == 0 ? pq0 : d == 1 ? pq1 : d == 2 ? pq2 : pq3);
-                if (d == 0) { l0 = 0.f; g.x = gp; }
-                else if (d == 1) { l1 = 0.f; g.y = gp; }
-                else if (d == 2) { l2 = 0.f; g.z = gp; }
-                else { l3 = 0.f; g.w = gp; }
-              }
-            }
-            if (DICE) {
-              const float4 db = *reinterpret_cast<const float4*>(s_db + c4);
-              g.x = fmaf(db.x, pq0, g.x);
-              g.y = fmaf(db.y, pq1, g.y);
-              g.z = fmaf(db.z, pq2, g.z);
-              g.w = fmaf(db.w, pq3, g.w);
-            }
-          } else {
-            // BCE / balanced BCE / none, optional dice
-            float4 wn = make_float4(1.f, 1.f, 1.f, 1.f), db = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (MODE == RN_CLS_BALANCED_BCE) wn = *reinterpret_cast<const float4*>(s_wneg + c4);
-            if (DICE) db = *reinterpret_cast<const float4*>(s_db + c4);
-            if (bulk) {
-              float p0, p1, p2, p3;
-              l0 = bce_neg_bulk(v.x, p0);
-              l1 = bce_neg_bulk(v.y, p1);
-              l2 = bce_neg_bulk(v.z, p2);
-              l3 = bce_neg_bulk(v.w, p3);
-              if (MODE == RN_CLS_NONE) {
-                l0 = l1 = l2 = l3 = 0.f;
-              } else {
-                const float k0 = inv_mc * wn.x, k1 = inv_mc * wn.y, k2 = inv_mc * wn.z, k3 = inv_mc * wn.w;
-                g.x = p0 * k0; g.y = p1 * k1; g.z = p2 * k2; g.w = p3 * k3;
-                if (MODE == RN_CLS_BALANCED_BCE) { l0 *= wn.x; l1 *= wn.y; l2 *= wn.z; l3 *= wn.w; }
-              }
-              if (DICE) {
-                g.x = fmaf(db.x, p0 * (1.0f - p0), g.x);
-                g.y = fmaf(db.y, p1 * (1.0f - p1), g.y);
-                g.z = fmaf(db.z, p2 * (1.0f - p2), g.z);
-                g.w = fmaf(db.w, p3 * (1.0f - p3), g.w);
-              }
-            } else {
-              const float xs[4] = {v.x, v.y, v.z, v.w};
-              float ls[4], gs[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float z = (d == (unsigned)k) ? 1.0f : 0.0f;
-                float loss = 0.f, pk = 0.f, dx = 0.f;
-                bce_elem<true>(xs[k], z, loss, pk, dx);
-                float gk = 0.f;
-                if (MODE == RN_CLS_NONE) {
-                  loss = 0.f;
-                } else {
-                  float wk = 1.0f;
-                  if (MODE == RN_CLS_BALANCED_BCE) wk = z == 1.0f ? s_wpos[c4 + k] : s_wneg[c4 + k];
-                  loss *= wk;
-                  gk = dx * (inv_mc * wk);
-                }
-                if (DICE) gk += (z * s_da[c4 + k] + s_db[c4 + k]) * (pk * (1.0f - pk));
-                ls[k] = loss;
-                gs[k] = gk;
-              }
-              l0 = ls[0]; l1 = ls[1]; l2 = ls[2]; l3 = ls[3];
-              g = make_float4(gs[0], gs[1], gs[2], gs[3]);
-            }
-          }
-          a0 += l0;
-          a1 += l1;
-          a2 += l2;
-          a3 += l3;
-        }
-        if (write_grad && (half == 0 || has1)) __stcs(gout + (half ? u1 : u), g);
-      }
     }
-    acc_neg += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+    acc_neg += ((double)acc4.x + (double)acc4.y) + ((double)acc4.z + (double)acc4.w);
   }
   // focal: negatives accumulated w^2 log(q+eps), loss = -(1-alpha) * that; BCE modes: plain sum
   double acc = MODE == RN_CLS_FOCAL ? acc_pos - (double)(1.0f - prm.alpha) * acc_neg : acc_pos + acc_neg;
@@ -994,22 +1028,39 @@ static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaS
     launch_cls<MODE, DICE, false>(vec4, grid, smem, st, segs, prm);
 }
 
+static unsigned gcd_u(unsigned a, unsigned b) {
+  while (b) {
+    const unsigned t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
 template <int MODE, bool DICE>
 static void launch_fast_variant(const Segs& segs, const FocalFastParams& fp, bool select, long long work,
                                 size_t smem, cudaStream_t st) {
-#define RN_LAUNCH_FF(MINB, SEL)                                                                          \
-  do {                                                                                                   \
-    const unsigned g = persistent_grid(cls_fast_kernel<MODE, DICE, MINB, SEL>, kLossThreads, smem, work); \
-    cls_fast_kernel<MODE, DICE, MINB, SEL><<<g, kLossThreads, smem, st>>>(segs, fp);                     \
+  // 4 resident CTAs of 256 threads per SM (64 registers): measured faster than 5 x 48 registers.
+  // The grid is the resident wave, rounded down to a multiple of cv / gcd(cv, 256) when that costs
+  // < 4 % of the CTAs, which makes every thread's float4 column constant (FIXED_COL).
+#define RN_LAUNCH_FF(SEL)                                                                                       \
+  do {                                                                                                          \
+    unsigned g = persistent_grid(cls_fast_kernel<MODE, DICE, 4, SEL, false>, kLossThreads, smem, work);         \
+    const unsigned q = (unsigned)fp.cv / gcd_u((unsigned)fp.cv, (unsigned)kLossThreads);                        \
+    const unsigned gf = g / q * q;                                                                              \
+    if (gf > 0 && (g - gf) * 25u <= g) {                                                                        \
+      cls_fast_kernel<MODE, DICE, 4, SEL, true><<<gf, kLossThreads, smem, st>>>(segs, fp);                      \
+    } else {                                                                                                    \
+      cls_fast_kernel<MODE, DICE, 4, SEL, false><<<g, kLossThreads, smem, st>>>(segs, fp);                      \
+    }                                                                                                           \
   } while (0)
-  // 4 resident CTAs of 256 threads per SM (64 registers): measured faster than 5 x 48 registers
-  if (select) RN_LAUNCH_FF(4, true); else RN_LAUNCH_FF(4, false);
+  if (select) RN_LAUNCH_FF(true); else RN_LAUNCH_FF(false);
 #undef RN_LAUNCH_FF
 }
 
 static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st) {
-  const long long work = (units + 1) / 2;
+  const long long work = (units + 3) / 4;
   const int base = mode & 15;
   const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
   const size_t smem = (dice || base == RN_CLS_BALANCED_BCE) ? 4 * (size_t)fp.num_classes * sizeof(float) : 0;
