@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument('--cls-mode', default='focal')
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-overlap', action='store_true', help='keep the detection tail on the main stream')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
     ap.add_argument('--opt', action='append', default=[], help='rn_set_option name=value (tuning knob)')
     ap.add_argument('--ref-budget-s', type=float, default=120.0, help='wall-clock budget of the reference arm')
@@ -321,8 +322,9 @@ def run_b200(args):
         return out
 
     path.stage_hook = timed
+    overlap = not args.no_overlap
     for _ in range(args.warmup):
-        path.step(gt_boxes, gt_classes, gt_counts, logits, regs)
+        path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
     barrier()
     sampler = ClockSampler('GPU-' + str(torch.cuda.get_device_properties(dev).uuid))
     if rank == 0:
@@ -332,7 +334,8 @@ def run_b200(args):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):
-        path.step(gt_boxes, gt_classes, gt_counts, logits, regs)
+        path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
+    path.join()          # the timed region ends when the last step's detections are done too
     end.record()
     barrier()
     record['on'] = False
@@ -433,6 +436,7 @@ def run_b200(args):
                          'peak_source': peak_src},
             'kernels': kernels,
             'fused_loss_select': bool(path.fused_select_supported()),
+            'detect_tail_on_side_stream': bool(overlap and path.fused_select_supported()),
             'cpu_baseline': cpu_baseline,
             'check': {'class_loss': loss_vals[0], 'regr_loss': loss_vals[1], 'num_fg': loss_vals[2],
                       'candidates': cand_total, 'detections': det_total},

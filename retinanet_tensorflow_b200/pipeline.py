@@ -78,6 +78,8 @@ class DenseHeadPath(object):
         self.out_capacity = int(out_capacity if out_capacity is not None else capacity)
         self.group = process_group
         self.stage_hook = None  # optional callable(stage_name, thunk) -> thunk(); bench.py times stages with it
+        self._side = None        # side stream for the detection tail (step(overlap_detect=True))
+        self._side_done = None
         self.pyr = pyramid_for(self.image_size, self.levels, anchor_size_mode, self.names)
         self.anchors = int(self.pyr.anchors_per_image)
         self.rows_total = self.batch * self.anchors
@@ -222,10 +224,11 @@ class DenseHeadPath(object):
         return bool(_lib.lib.rn_fused_select_supported(self.num_classes, self.mode, self.focus, C.byref(self.rows))) \
             and 0.0 < self.score_thr < 1.0
 
-    def loss_and_select(self, logits, regression, want_grad=True):
+    def loss_and_select(self, logits, regression, want_grad=True, finalize=True):
         """`loss()` and `select()` on the same logits with the [rows, C] tensor read ONCE: the
         focal kernel also pre-selects the anchors whose best class probability exceeds score_thr
-        (training step that also produces detections, train.py:218-220 + 68-75)."""
+        (training step that also produces detections, train.py:218-220 + 68-75).
+        finalize=False leaves the candidates unordered in the workspace (call select_finalize)."""
         if not self.fused_select_supported():
             self.loss(logits, regression, want_grad)
             self.select(logits, regression)
@@ -258,11 +261,19 @@ class DenseHeadPath(object):
             self._huber_ws.numel(), st))
         self._allreduce(self.stats[_lib.RN_STAT_CLS_SUM:_lib.RN_STAT_HUBER_SUM + 1])
         _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
+        if finalize:
+            self.select_finalize(regression)
+        return self.loss_out, self.cand_count
+
+    def select_finalize(self, regression):
+        """Order / de-duplicate / decode the candidates the fused pass left in the workspace."""
+        m_reg, _ = self._maps(regression, 4)
         self._stage('select', lambda: _lib.call(
             'rn_select_finalize', C.byref(self.pyr), self.batch, C.byref(m_reg), 1, self.topk_per_level,
             self.capacity, 1, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
-            _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self._sel_ws), self._sel_ws_bytes, st))
-        return self.loss_out, self.cand_count
+            _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self._sel_ws), self._sel_ws_bytes,
+            _lib.stream_ptr()))
+        return self.cand_count
 
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
@@ -291,20 +302,52 @@ class DenseHeadPath(object):
         return self.det_boxes, self.det_scores, self.det_classes, self.det_count
 
     # ---- one whole step of the hot path -----------------------------------------------------
-    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True):
+    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True, overlap_detect=False):
         """assign -> loss fwd+bwd -> decode/select/NMS.  With `fused` (default) and a supported
-        configuration the loss kernel also does the candidate selection (logits read once)."""
+        configuration the loss kernel also does the candidate selection (logits read once).
+
+        overlap_detect=True puts the latency-bound tail (candidate finalize + NMS, one CTA per
+        image) on a side stream so that it overlaps the next step's assignment and loss kernels;
+        events keep the select workspace from being overwritten early.  Detections are then valid
+        after `join()` (or a device synchronize); losses and gradients are on the current stream
+        as always."""
         self.assign(gt_boxes, gt_classes, gt_counts)
-        if fused and self.fused_select_supported():
-            self.loss_and_select(logits, regression)
-        else:
+        if not (fused and self.fused_select_supported()):
+            self.join()
             self.loss(logits, regression)
             self.select(logits, regression)
-        self.nms()
+            self.nms()
+            return self.loss_out, self.det_count
+        main = torch.cuda.current_stream()
+        if self._side_done is not None:
+            main.wait_event(self._side_done)   # previous tail has consumed the select workspace
+            self._side_done = None
+        self.loss_and_select(logits, regression, finalize=False)
+        if not overlap_detect:
+            self.select_finalize(regression)
+            self.nms()
+            return self.loss_out, self.det_count
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)  # small CTAs first
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            self.select_finalize(regression)
+            self.nms()
+            self._side_done = torch.cuda.Event()
+            self._side_done.record(self._side)
         return self.loss_out, self.det_count
+
+    def join(self):
+        """Make the current stream wait for an overlapped detection tail."""
+        if self._side_done is not None:
+            torch.cuda.current_stream().wait_event(self._side_done)
+            self._side_done = None
 
     def check_status(self, ignore=0):
         """Synchronising: raises what the reference's runtime asserts would have raised."""
+        self.join()
         word = int(self.status.item())
         self.status.zero_()
         raise_for_status(word, ignore)

@@ -176,6 +176,38 @@ def test_fused_loss_and_select_equals_separate_passes(name, batch, mode):
     assert int(path.cand_classes[77 // path.anchors][path.cand_anchor[77 // path.anchors] == b77]) == 1
 
 
+def test_overlapped_detection_tail_gives_the_same_results():
+    """step(overlap_detect=True) over several steps with changing inputs == the serial step."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    wl, path, logits, regs = _case('voc', 2, capacity=8192)
+    boxes, classes, counts = synthetic.gt_batch(wl, 2)
+    gt = [torch.from_numpy(x).cuda() for x in (boxes, classes, counts)]
+    inputs = [(logits + 0.05 * i, regs * (1.0 + 0.01 * i)) for i in range(4)]
+    want = []
+    for lg, rg in inputs:
+        path.step(*gt, lg, rg)
+        torch.cuda.synchronize()
+        want.append((path.loss_out.clone(), path.det_count.clone(), path.det_index.clone(), path.det_boxes.clone()))
+    got = []
+    for lg, rg in inputs:      # back to back, no host synchronisation between steps
+        path.step(*gt, lg, rg, overlap_detect=True)
+        path.join()            # results of THIS step (still asynchronous w.r.t. the host)
+        got.append((path.loss_out.clone(), path.det_count.clone(), path.det_index.clone(), path.det_boxes.clone()))
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1])
+        for b in range(2):
+            m = int(w[1][b])
+            assert torch.equal(w[2][b, :m], g[2][b, :m]) and torch.equal(w[3][b, :m], g[3][b, :m])
+    # and fully pipelined (join only at the end): the last step's detections must be right
+    for lg, rg in inputs:
+        path.step(*gt, lg, rg, overlap_detect=True)
+    path.join()
+    torch.cuda.synchronize()
+    assert torch.equal(path.det_count, want[-1][1]) and torch.equal(path.loss_out, want[-1][0])
+
+
 def test_topk_per_level_prefilter():
     """Extension (not in the reference): k best per (image, level), identity for large k."""
     import torch
