@@ -248,6 +248,12 @@ RN_API int rn_cls_loss_elementwise(int64_t rows, int num_classes, const float* d
                                    float eps, const float* d_w_pos, const float* d_w_neg,
                                    float* d_loss, float* d_grad, void* stream);
 
+/* losses.focal_softmax_cross_entropy_with_logits (losses.py:19-34): per-row loss [rows] and
+ * (optional) d loss[row] / d logits [rows, C]. */
+RN_API int rn_focal_softmax(int64_t rows, int num_classes, const float* d_labels,
+                            const float* d_logits, float focus, float alpha, float eps,
+                            float* d_loss, float* d_grad, void* stream);
+
 /* Backward of a loss of the per-class sums I_c = sum_m z p and P_c = sum_m p (dice_loss,
  * jaccard_loss, fixed_iou_loss; losses.py:37-73): grad[m,c] = (z*a[c] + b[c]) * p (1 - p),
  * with a = dL/dI and b = dL/dP supplied per class. */

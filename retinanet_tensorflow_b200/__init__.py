@@ -5,4 +5,4 @@ module surface: `levels`, `dataset`, `utils`, `losses` (+ `pipeline.DenseHeadPat
 batched form).  There is no CPU fallback: importing the compute modules without the built
 library raises."""
 
-__all__ = ['levels', 'dataset', 'utils', 'losses', 'augmentation', 'pipeline', 'dist', 'synthetic']
+__all__ = ['levels', 'dataset', 'utils', 'losses', 'augmentation', 'metrics', 'pipeline', 'dist', 'synthetic']

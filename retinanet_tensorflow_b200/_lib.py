@@ -95,6 +95,7 @@ PROTOTYPES = {
     'rn_huber_rows': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_loss_finalize': (_i, [_i, _i, _vp, _vp, _vp]),
     'rn_cls_loss_elementwise': (_i, [_i64, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    'rn_focal_softmax': (_i, [_i64, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
     'rn_colsum_backward': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rn_sigmoid': (_i, [_i64, _vp, _vp, _vp]),
     'rn_decode_boxes': (_i, [_PP, _i, _MP, _MP, _vp]),

@@ -970,6 +970,61 @@ __global__ void colsum_backward_kernel(long long n, int C, const float* __restri
   }
 }
 
+// losses.focal_softmax_cross_entropy_with_logits (losses.py:19-34): one warp per row.
+//   prob = softmax(x);  a = z==1 ? alpha : 1-alpha;  pt = z==1 ? prob : 1-prob
+//   loss[row] = -sum_c a * (1-pt)^focus * z * log(prob + eps)
+// grad[row, j] = p_j (D_j - sum_c D_c p_c) with D_c = d loss / d prob_c.
+__global__ void focal_softmax_kernel(long long rows, int C, const float* __restrict__ labels,
+                                     const float* __restrict__ logits, float focus, float alpha, float eps,
+                                     float* __restrict__ loss_out, float* __restrict__ grad_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float* x = logits + r * C;
+    const float* z = labels + r * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(x[c] - mx);
+    se = warp_sum(se);
+    float loss = 0.f, dot = 0.f;   // dot = sum_c D_c p_c
+    for (int c = lane; c < C; c += 32) {
+      const float p = fdiv(expf(x[c] - mx), se);
+      const float zc = z[c];
+      const bool is1 = zc == 1.0f;
+      const float a = is1 ? alpha : 1.0f - alpha;
+      const float pt = is1 ? p : 1.0f - p;
+      const float w = 1.0f - pt;
+      const float pe = p + eps;
+      const float lg = logf(pe);
+      const float mod = powf(w, focus);
+      loss -= a * mod * zc * lg;
+      const float dmod = focus * powf(w, focus - 1.0f) * (is1 ? -1.0f : 1.0f);   // d (1-pt)^f / d p
+      const float D = -a * zc * (dmod * lg + mod / pe);
+      dot += D * p;
+    }
+    loss = warp_sum(loss);
+    dot = warp_sum(dot);
+    if (lane == 0 && loss_out) loss_out[r] = loss;
+    if (grad_out) {
+      for (int c = lane; c < C; c += 32) {
+        const float p = fdiv(expf(x[c] - mx), se);
+        const float zc = z[c];
+        const bool is1 = zc == 1.0f;
+        const float a = is1 ? alpha : 1.0f - alpha;
+        const float pt = is1 ? p : 1.0f - p;
+        const float w = 1.0f - pt;
+        const float pe = p + eps;
+        const float dmod = focus * powf(w, focus - 1.0f) * (is1 ? -1.0f : 1.0f);
+        const float D = -a * zc * (dmod * logf(pe) + powf(w, focus) / pe);
+        grad_out[r * C + c] = p * (D - dot);
+      }
+    }
+  }
+}
+
 __global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = sigmoid_f32(in[i]);
@@ -1425,6 +1480,17 @@ extern "C" int rn_colsum_backward(int64_t rows, int num_classes, const float* d_
   colsum_backward_kernel<<<loss_grid(n, 256, 16), 256, 0, (cudaStream_t)stream>>>(n, num_classes, d_labels, d_logits,
                                                                                  d_a, d_b, d_grad);
   RN_CUDA_CHECK_LAUNCH("rn_colsum_backward");
+  return RN_OK;
+}
+
+extern "C" int rn_focal_softmax(int64_t rows, int num_classes, const float* d_labels, const float* d_logits,
+                                float focus, float alpha, float eps, float* d_loss, float* d_grad, void* stream) {
+  RN_REQUIRE(rows >= 0 && num_classes >= 1, RN_ERR_BAD_ARG, "rn_focal_softmax: bad shape");
+  if (rows == 0) return RN_OK;
+  RN_REQUIRE(d_labels && d_logits && (d_loss || d_grad), RN_ERR_BAD_ARG, "rn_focal_softmax: NULL pointer");
+  focal_softmax_kernel<<<loss_grid(rows * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+      rows, num_classes, d_labels, d_logits, focus, alpha, eps, d_loss, d_grad);
+  RN_CUDA_CHECK_LAUNCH("rn_focal_softmax");
   return RN_OK;
 }
 

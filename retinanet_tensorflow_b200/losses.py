@@ -63,6 +63,30 @@ def focal_sigmoid_cross_entropy_with_logits(labels, logits, focus=2.0, alpha=0.2
     return _Elementwise.apply(labels, as_cuda(logits), _lib.RN_CLS_FOCAL, focus, alpha, eps, None, None)
 
 
+class _FocalSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, logits, focus, alpha, eps):
+        labels, logits, rows, c = _two_d(labels, logits)
+        loss = torch.empty(logits.shape[:-1], dtype=torch.float32, device=logits.device)
+        grad = torch.empty_like(logits)
+        _lib.call('rn_focal_softmax', rows, c, _lib.ptr(labels), _lib.ptr(logits), float(focus), float(alpha),
+                  float(eps), _lib.ptr(loss), _lib.ptr(grad), _lib.stream_ptr())
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return None, g.unsqueeze(-1) * grad, None, None, None
+
+
+def focal_softmax_cross_entropy_with_logits(labels, logits, focus=2.0, alpha=0.25, eps=1e-7,
+                                            name='focal_softmax_cross_entropy_with_logits'):
+    """-sum_c a_c (1 - p_t,c)^focus z_c log(softmax(x)_c + eps), one value per row (losses.py:19-34;
+    unused by the reference's classification_loss and marked "TODO: check if this is correct" there)."""
+    return _FocalSoftmax.apply(labels, as_cuda(logits), focus, alpha, eps)
+
+
 def sigmoid_cross_entropy_with_logits(labels, logits):
     """tf.nn.sigmoid_cross_entropy_with_logits as called at losses.py:107,124."""
     return _Elementwise.apply(labels, as_cuda(logits), _lib.RN_CLS_BCE, 2.0, 0.25, 1e-7, None, None)

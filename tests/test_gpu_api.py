@@ -318,3 +318,44 @@ def test_process_labels_and_logits_matches_oracle():
             np.testing.assert_array_equal(_np(gt.classification.unscaled), wt.classification.unscaled)
         else:
             assert gt.classification.unscaled is None
+
+
+def test_focal_softmax_matches_oracle_and_autograd():
+    import torch
+    from retinanet_tensorflow_b200 import losses
+    z, x = _loss_inputs(200, 7, seed=12)
+    xt = torch.tensor(x, device='cuda', requires_grad=True)
+    got = losses.focal_softmax_cross_entropy_with_logits(z, xt)
+    want = oracle.focal_softmax_cross_entropy_with_logits(z, x)
+    assert got.shape == (200,)
+    helpers.assert_close(_np(got), want, rtol=1e-5, atol=1e-8, what='focal softmax')
+    got.sum().backward()
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    z64 = torch.tensor(z, dtype=torch.float64)
+    p = torch.softmax(x64, -1)
+    a = torch.where(z64 == 1, torch.tensor(0.25, dtype=torch.float64), torch.tensor(0.75, dtype=torch.float64))
+    pt = torch.where(z64 == 1, p, 1 - p)
+    val = -(a * (1 - pt) ** 2.0 * z64 * torch.log(p + 1e-7)).sum()
+    (g,) = torch.autograd.grad(val, x64)
+    helpers.assert_close(_np(xt.grad), g.numpy(), rtol=2e-5, atol=1e-6 * np.abs(g.numpy()).max(), what='grad')
+
+
+def test_dormant_metrics():
+    """train.py:137-161 (regr_iou / class_iou), composed from the drop-in functions."""
+    import torch
+    from retinanet_tensorflow_b200 import metrics
+    rng = np.random.default_rng(13)
+    z, x = _loss_inputs(400, 5, seed=14)
+    tl = rng.uniform(0, 0.5, (400, 2))
+    lab_boxes = np.concatenate([tl, tl + rng.uniform(0.05, 0.4, (400, 2))], -1).astype(np.float32)
+    pred_boxes = (lab_boxes + rng.normal(0, 0.01, lab_boxes.shape)).astype(np.float32)
+    pred_boxes[:, 2:] = np.maximum(pred_boxes[:, 2:], pred_boxes[:, :2] + 1e-3)
+    got = float(metrics.regr_iou(z, lab_boxes, pred_boxes))
+    a = oracle.boxes_decode(z, lab_boxes)
+    b = oracle.boxes_decode(z, pred_boxes)
+    want = float(oracle.iou(a.boxes, b.boxes).astype(np.float64).mean())
+    assert abs(got - want) < 1e-6 and 0.5 < got <= 1.0
+    ci = float(metrics.class_iou(z, x))
+    pz, zz = oracle.sigmoid(x) > 0.5, z > 0.5
+    want_ci = np.mean([((zz == c) & (pz == c)).sum() / max(((zz == c) | (pz == c)).sum(), 1) for c in (False, True)])
+    assert abs(ci - want_ci) < 1e-6
