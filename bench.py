@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument('--cls-mode', default='focal')
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'],
+                    help='multi-GPU statistics exchange: own kernel over NVLink peer memory, or NCCL')
     ap.add_argument('--no-overlap', action='store_true', help='keep the detection tail on the main stream')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
     ap.add_argument('--opt', action='append', default=[], help='rn_set_option name=value (tuning knob)')
@@ -293,7 +295,8 @@ def run_b200(args):
 
     # ---- inputs resident in HBM
     path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, cls_mode=args.cls_mode,
-                         capacity=8192, process_group=None if world > 1 else False, device=dev)
+                         capacity=8192, process_group=None if world > 1 else False, device=dev,
+                         exchange=args.exchange)
     gt_boxes_h, gt_classes_h, gt_counts_h = synthetic.gt_batch(wl, batch, first_image=rank * batch)
     gt_boxes = torch.from_numpy(gt_boxes_h).to(dev)
     gt_classes = torch.from_numpy(gt_classes_h).to(dev)
@@ -436,6 +439,7 @@ def run_b200(args):
                          'peak_source': peak_src},
             'kernels': kernels,
             'fused_loss_select': bool(path.fused_select_supported()),
+            'stats_exchange': ('peer-memory kernel' if path._peer is not None else 'nccl') if world > 1 else None,
             'detect_tail_on_side_stream': bool(overlap and path.fused_select_supported()),
             'cpu_baseline': cpu_baseline,
             'check': {'class_loss': loss_vals[0], 'regr_loss': loss_vals[1], 'num_fg': loss_vals[2],

@@ -62,6 +62,7 @@ typedef enum rn_status {
 #define RN_FLAG_IOU_RANGE 2u      /* IoU NaN or outside [0,1]  (utils.py:94)                  */
 #define RN_FLAG_CAND_OVERFLOW 4u  /* more candidates than `capacity`; extra ones dropped      */
 #define RN_FLAG_DET_OVERFLOW 8u   /* more detections than `out_capacity`; extra ones dropped  */
+#define RN_FLAG_EXCHANGE_TIMEOUT 32u /* a peer's message did not arrive within ~2 s (rn_stats_exchange) */
 #define RN_FLAG_EMPTY_GT 16u      /* an image had 0 GT boxes (reference asserts >= 1,
                                      data_loaders/inferred.py:30); handled as all-background  */
 
@@ -260,6 +261,20 @@ RN_API int rn_focal_softmax(int64_t rows, int num_classes, const float* d_labels
 RN_API int rn_colsum_backward(int64_t rows, int num_classes, const float* d_labels,
                               const float* d_logits, const float* d_a, const float* d_b,
                               float* d_grad, void* stream);
+
+/* ---- multi-GPU exchange over NVLink peer memory -------------------------------------------- */
+/* All-reduce(sum) of d_stats[offset : offset + len) across `world` ranks WITHOUT a collective
+ * library: every rank owns a mailbox of rn_stats_mailbox_bytes() in peer-mapped memory (zeroed
+ * once); d_peer_mailboxes is a DEVICE array of the `world` mailbox base pointers as mapped into
+ * this process (e.g. torch symmetric memory's buffer_ptrs, cuMem/IPC mappings).  One small
+ * kernel stores the slice into every peer, publishes `epoch` (must increase by 1 per use of a
+ * phase; use slot = 2 * phase + (epoch & 1) so that a slot is never rewritten before it is read),
+ * waits for all ranks' messages and sums them in rank order: results are bit-identical on all
+ * ranks.  A peer that never arrives sets RN_FLAG_EXCHANGE_TIMEOUT after ~2 s instead of hanging. */
+RN_API size_t rn_stats_mailbox_bytes(int world, int len_max, int slots);
+RN_API int rn_stats_exchange(double* d_stats, int offset, int len, int len_max, int world, int rank,
+                             const void* const* d_peer_mailboxes, int slot, int slots, uint64_t epoch,
+                             uint32_t* d_status, void* stream);
 
 /* ---- decode + select + NMS ------------------------------------------------------------ */
 /* tf.nn.sigmoid (utils.py:249) with the same device function the fused kernels use. */

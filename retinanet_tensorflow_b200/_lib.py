@@ -27,6 +27,7 @@ RN_BOXOP_DECODE, RN_BOXOP_ADD_CENTRE, RN_BOXOP_SCALE = 0, 1, 2
 RN_BOXOP_CENTRE_TO_CORNER, RN_BOXOP_CORNER_TO_CENTRE = 3, 4
 
 RN_FLAG_BOX_ORDER, RN_FLAG_IOU_RANGE, RN_FLAG_CAND_OVERFLOW, RN_FLAG_DET_OVERFLOW, RN_FLAG_EMPTY_GT = 1, 2, 4, 8, 16
+RN_FLAG_EXCHANGE_TIMEOUT = 32
 
 
 class Level(C.Structure):
@@ -98,6 +99,8 @@ PROTOTYPES = {
     'rn_focal_softmax': (_i, [_i64, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
     'rn_colsum_backward': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rn_sigmoid': (_i, [_i64, _vp, _vp, _vp]),
+    'rn_stats_mailbox_bytes': (_sz, [_i, _i, _i]),
+    'rn_stats_exchange': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, C.c_uint64, _vp, _vp]),
     'rn_decode_boxes': (_i, [_PP, _i, _MP, _MP, _vp]),
     'rn_boxmap_op': (_i, [_PP, _i, _i, _MP, _MP, _vp]),
     'rn_classmap_fg': (_i, [_i64, _i, _vp, _f, _vp, _vp]),

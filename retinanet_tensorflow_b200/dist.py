@@ -62,3 +62,54 @@ def finalize(stats, num_classes, mode):
         cls = cls + (1.0 - 2.0 * inter / (npos + psum)).mean()
     reg = s[_lib.RN_STAT_HUBER_SUM] / (4.0 * nfg) if float(nfg) > 0 else s.new_zeros(())
     return cls, reg, nfg, m
+
+
+PHASES = {'counts': 0, 'dice_sums': 1, 'loss_sums': 2}
+
+
+def phase_slice(phase, num_classes):
+    """(offset, length) of the stats-vector slice a phase exchanges."""
+    sl = slices(num_classes)[phase]
+    return sl.start, sl.stop - sl.start
+
+
+class PeerExchange(object):
+    """The stats all-reduce as this library's own kernel over NVLink peer memory
+    (`rn_stats_exchange`): every rank stores its slice into every peer's symmetric-memory mailbox,
+    publishes an epoch flag and sums the `world` messages in rank order.  No NCCL call on the step's
+    critical path; results are bit-identical on all ranks.  Needs torch symmetric memory
+    (CUDA VMM peer mappings inside one NVLink domain)."""
+
+    SLOTS = 6  # 3 phases x epoch parity
+
+    def __init__(self, num_classes, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        tdist = torch.distributed
+        self.group = group if group is not None else tdist.group.WORLD
+        self.world = tdist.get_world_size(self.group)
+        self.rank = tdist.get_rank(self.group)
+        self.num_classes = int(num_classes)
+        self.len_max = stats_length(num_classes)
+        nbytes = int(_lib.lib.rn_stats_mailbox_bytes(self.world, self.len_max, self.SLOTS))
+        self.buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
+            raise RuntimeError('symmetric-memory rendezvous returned unexpected peer pointers')
+        self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.epochs = [0, 0, 0]
+        torch.cuda.synchronize(device)
+        tdist.barrier(self.group)     # every mailbox is zeroed before anybody posts
+        self._C = C
+
+    def all_reduce(self, stats, phase, status=None):
+        k = PHASES[phase]
+        self.epochs[k] += 1
+        epoch = self.epochs[k]
+        offset, length = phase_slice(phase, self.num_classes)
+        _lib.call('rn_stats_exchange', _lib.ptr(stats), offset, length, self.len_max, self.world, self.rank,
+                  _lib.ptr(self.peer_ptrs), 2 * k + (epoch & 1), self.SLOTS, epoch, _lib.ptr(status),
+                  _lib.stream_ptr())
+        return stats

@@ -41,6 +41,7 @@ _FLAG_MESSAGES = {
     _lib.RN_FLAG_CAND_OVERFLOW: 'more candidates than `capacity`',
     _lib.RN_FLAG_DET_OVERFLOW: 'more detections than `out_capacity`',
     _lib.RN_FLAG_EMPTY_GT: 'an image has no ground-truth box (data_loaders/inferred.py:30)',
+    _lib.RN_FLAG_EXCHANGE_TIMEOUT: 'a peer rank did not post its statistics within ~2 s',
 }
 
 
@@ -57,7 +58,7 @@ class DenseHeadPath(object):
     def __init__(self, image_size, num_classes, batch, max_gt, levels=None, *, cls_mode='focal',
                  anchor_size_mode='tf1_int_trunc', neg_iou=0.4, pos_iou=0.5, focus=2.0, alpha=0.25, eps=1e-7,
                  score_thr=0.5, nms_iou=0.5, max_output_per_class=1000, topk_per_level=0, capacity=4096,
-                 out_capacity=None, keep_iou=False, device=None, process_group=None):
+                 out_capacity=None, keep_iou=False, device=None, process_group=None, exchange='auto'):
         self.device = _lib.require_cuda(device)
         self.levels = build_levels() if levels is None else levels
         self.names = list(self.levels)
@@ -77,6 +78,8 @@ class DenseHeadPath(object):
         self.capacity = int(capacity)
         self.out_capacity = int(out_capacity if out_capacity is not None else capacity)
         self.group = process_group
+        self.exchange = exchange   # 'nccl' | 'peer' (own kernel over NVLink peer memory) | 'auto'
+        self._peer = None
         self.stage_hook = None  # optional callable(stage_name, thunk) -> thunk(); bench.py times stages with it
         self._side = None        # side stream for the detection tail (step(overlap_detect=True))
         self._side_done = None
@@ -158,9 +161,30 @@ class DenseHeadPath(object):
         """Per-level `[B, H, W, A, width]` views of a merged buffer for an explicit pyramid/batch."""
         return split_merged(pyr, batch, merged, (width,))
 
-    def _allreduce(self, t):
-        """Sum a slice of the stats vector over the ranks (process_group=False disables)."""
-        dist.all_reduce_sum(t, self.group)
+    def _multi_rank(self):
+        d = torch.distributed
+        return self.group is not False and d.is_available() and d.is_initialized() and d.get_world_size(
+            self.group if self.group is not None else None) > 1
+
+    def _allreduce(self, phase):
+        """Sum one slice of the stats vector over the ranks ('counts' | 'dice_sums' | 'loss_sums').
+        process_group=False disables.  exchange='peer' uses rn_stats_exchange (this library's kernel
+        over NVLink peer memory), 'nccl' torch.distributed.all_reduce, 'auto' tries peer first."""
+        if not self._multi_rank():
+            return
+        if self.exchange in ('peer', 'auto') and self._peer is None:
+            try:
+                self._peer = dist.PeerExchange(self.num_classes, self.device, self.group)
+            except Exception as err:  # symmetric memory unavailable: fall back to the collective library
+                if self.exchange == 'peer':
+                    raise
+                import warnings
+                warnings.warn('peer-memory exchange unavailable (%s); using NCCL all-reduce' % (err,))
+                self.exchange = 'nccl'
+        if self._peer is not None and self.exchange != 'nccl':
+            self._peer.all_reduce(self.stats, phase, self.status)
+        else:
+            dist.all_reduce_sum(self.stats[dist.slices(self.num_classes)[phase]], self.group)
 
     def _stage(self, name, fn):
         return fn() if self.stage_hook is None else self.stage_hook(name, fn)
@@ -183,7 +207,7 @@ class DenseHeadPath(object):
             self.max_gt, self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched),
             C.byref(self._m_label), C.byref(self._m_deltas), C.byref(self._m_iou), _lib.ptr(self.stats),
             _lib.ptr(self.status), _lib.stream_ptr()))
-        self._allreduce(self.stats)
+        self._allreduce('counts')
         return self.label, self.deltas
 
     # ---- stage 2: loss forward + backward (utils.process_labels_and_logits + losses.loss) ---
@@ -206,7 +230,7 @@ class DenseHeadPath(object):
             self._stage('cls_sums', lambda: _lib.call(
                 'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
                 _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
-            self._allreduce(self.stats[_lib.RN_STATS_HEADER + Cn:])
+            self._allreduce('dice_sums')
         self._stage('cls_loss', lambda: _lib.call(
             'rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, self.mode,
             self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
@@ -215,7 +239,7 @@ class DenseHeadPath(object):
             'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
             C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
             self._huber_ws.numel(), st))
-        self._allreduce(self.stats[_lib.RN_STAT_CLS_SUM:_lib.RN_STAT_HUBER_SUM + 1])
+        self._allreduce('loss_sums')
         _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
         return self.loss_out
 
@@ -249,7 +273,7 @@ class DenseHeadPath(object):
             self._stage('cls_sums', lambda: _lib.call(
                 'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
                 _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
-            self._allreduce(self.stats[_lib.RN_STATS_HEADER + Cn:])
+            self._allreduce('dice_sums')
         self._stage('cls_loss', lambda: _lib.call(
             'rn_cls_loss_select', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode,
             self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
@@ -259,7 +283,7 @@ class DenseHeadPath(object):
             'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
             C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
             self._huber_ws.numel(), st))
-        self._allreduce(self.stats[_lib.RN_STAT_CLS_SUM:_lib.RN_STAT_HUBER_SUM + 1])
+        self._allreduce('loss_sums')
         _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
         if finalize:
             self.select_finalize(regression)

@@ -22,7 +22,7 @@ from retinanet_tensorflow_b200.pipeline import DenseHeadPath
 def run(wl, first, count, group, mode, logits=None, regs=None):
     boxes, classes, counts = synthetic.gt_batch(wl, count, first_image=first)
     path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, count, wl.max_gt, cls_mode=mode,
-                         process_group=group, capacity=8192)
+                         process_group=group, capacity=8192, exchange=os.environ.get('RN_EXCHANGE', 'auto'))
     gb, gc, gn = (torch.from_numpy(x).cuda() for x in (boxes, classes, counts))
     if logits is None:
         single = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, count, wl.max_gt, process_group=False)
@@ -77,8 +77,9 @@ def main():
             if not torch.equal(det, whole.det_count.cpu()):
                 ok = False
                 print('MISMATCH det_count', mode)
-            print('mode %-13s world %d: loss %s  (single-GPU %s)' % (mode, world, shards[0][6][:2].tolist(),
-                                                                     want[:2].tolist()))
+            print('mode %-13s world %d exchange %s: loss %s  (single-GPU %s)' % (
+                mode, world, path.exchange if path._peer is None else 'peer', shards[0][6][:2].tolist(),
+                want[:2].tolist()))
     flag = torch.tensor([1 if ok else 0], device='cuda')
     tdist.broadcast(flag, 0)
     tdist.barrier()
