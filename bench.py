@@ -431,7 +431,7 @@ def run_b200(args):
                     'note': 'pinned host buffers -> H2D of GT + logits + regression preds, whole path, D2H of losses '
                             '+ detections; PCIe-bound (%.2f GB in per step)' % (h2d / 1e9)},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': 'cls_loss_kernel (fused sigmoid-focal fwd+bwd)',
+            'roofline': {'bound': 'hbm', 'kernel': 'cls_fast_kernel (fused sigmoid-focal fwd+bwd + candidate pre-selection)',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': (achieved / peak) if achieved else None,
                          'traffic': ncu_traffic('%s_b%d_%s' % (wl.name, batch, args.cls_mode)),

@@ -84,6 +84,11 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
       g = make_float4(fsub(cy, sh * 0.5f), fsub(cx, sw * 0.5f), fadd(cy, sh * 0.5f), fadd(cx, sw * 0.5f));
       if (i < n_gt) {
         if (!(g.x <= g.z && g.y <= g.w)) flags |= RN_FLAG_BOX_ORDER;  // utils.py:67
+        // utils.py:94 (0 <= iou <= 1): anchors have positive finite area, so an IoU can only leave
+        // [0, 1] or be NaN when a GT coordinate is not finite -- checked here once per box instead of
+        // once per pair.
+        if (!(fabsf(g.x) <= 3.0e38f && fabsf(g.y) <= 3.0e38f && fabsf(g.z) <= 3.0e38f && fabsf(g.w) <= 3.0e38f))
+          flags |= RN_FLAG_IOU_RANGE;
         keep = !(g.z < T0 || g.x > T2 || g.w < T1 || g.y > T3);
         if (i == 0) {
           s_ctr0 = ctr;
@@ -153,10 +158,8 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
         const float inter = fmul(fsub(yb, yt), fsub(xr, xl));
         const float uni = fsub(fadd(aa[k], ga), inter);
         const float approx = inter * rcp_approx(uni);
-        if (!(approx >= 0.f && approx <= 1.001f)) flags |= RN_FLAG_IOU_RANGE;  // utils.py:94 (NaN, < 0, > 1)
         if (approx * 1.000002f > best[k]) {
           const float v = fdiv(inter, uni);
-          if (!(v <= 1.f)) flags |= RN_FLAG_IOU_RANGE;
           if (v > best[k]) {
             best[k] = v;
             bestj[k] = j;

@@ -1,0 +1,60 @@
+"""Small end-to-end run for compute-sanitizer (not collected by pytest):
+
+    compute-sanitizer --tool memcheck  python tests/sanitize_check.py
+    compute-sanitizer --tool racecheck python tests/sanitize_check.py
+
+Exercises every kernel family on small shapes: assign, fused/unfused losses in all modes, dice
+sums, Huber, select (+fused), finalize with dedup and top-k, NMS, flip, box-map ops, dense labels,
+elementwise losses."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from retinanet_tensorflow_b200 import augmentation, dataset, losses, synthetic, utils
+from retinanet_tensorflow_b200.levels import build_levels
+from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+
+
+def main():
+    for name, classes in (('shapes', 3), ('voc', 20)):
+        wl = synthetic.WORKLOADS[name]
+        wl = synthetic.Workload(wl.name, wl.config, 192, 256, classes, wl.max_gt, 2)
+        boxes, cls, counts = synthetic.gt_batch(wl, 2)
+        gt = [torch.from_numpy(x).cuda() for x in (boxes, cls, counts)]
+        for mode in ('focal', 'bce_dice', 'balanced_bce', 'focal_dice'):
+            path = DenseHeadPath((wl.image_h, wl.image_w), classes, 2, wl.max_gt, cls_mode=mode, capacity=4096,
+                                 topk_per_level=50, keep_iou=True, process_group=False)
+            path.assign(*gt)
+            logits, regs = synthetic.head_outputs(path.label, path.deltas, classes, seed=1, device='cuda')
+            logits.view(-1, classes)[3, :min(3, classes)] = 3.0
+            path.step(*gt, logits, regs)
+            path.step(*gt, logits, regs, overlap_detect=True)
+            path.join()
+            path.loss(logits, regs)
+            path.detect(logits, regs)
+            augmentation.flip_compact(path.pyr, 2, path.label, path.deltas)
+            torch.cuda.synchronize()
+            path.check_status(ignore=12)
+    b, c = synthetic.gt_for_image(synthetic.WORKLOADS['shapes'], 0)
+    dataset.build_labels([128, 160], c, b, build_levels(), 3)
+    rng = np.random.default_rng(0)
+    z = (rng.uniform(size=(64, 5)) > 0.9).astype(np.float32)
+    x = torch.tensor(rng.normal(-2, 2, (64, 5)).astype(np.float32), device='cuda', requires_grad=True)
+    total = (losses.focal_sigmoid_cross_entropy_with_logits(z, x).sum() + losses.dice_loss(z, x, axis=0).sum() +
+             losses.classification_loss(z, x, z.max(-1) > 0.5) + losses.focal_softmax_cross_entropy_with_logits(z, x).sum())
+    total.backward()
+    probs = rng.uniform(0, 0.7, (6, 7, 9, 4)).astype(np.float32)
+    bx = np.concatenate([rng.uniform(0, .4, (6, 7, 9, 2)), rng.uniform(.5, 1, (6, 7, 9, 2))], -1).astype(np.float32)
+    utils.nms_classwise(utils.boxes_decode(probs, bx), 4)
+    utils.iou(bx, bx)
+    torch.cuda.synchronize()
+    print('SANITIZE_RUN_DONE')
+
+
+if __name__ == '__main__':
+    main()

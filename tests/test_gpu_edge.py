@@ -175,3 +175,16 @@ def test_zero_batch_and_argument_errors():
         path.loss(torch.zeros((7, 4), device='cuda'), torch.zeros((path.rows_total, 4), device='cuda'))
     with pytest.raises(ValueError):
         DenseHeadPath((128, 128), 4, 1, 4, cls_mode='nope', process_group=False)
+
+
+def test_non_finite_gt_is_flagged():
+    """utils.py:94: a NaN / infinite IoU fails the reference's 0 <= iou <= 1 assert."""
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    path = DenseHeadPath((128, 128), 3, 1, 2, process_group=False)
+    boxes = torch.tensor([[[0.1, 0.1, float('inf'), 0.5], [0.1, 0.1, 0.6, 0.6]]], dtype=torch.float32).cuda()
+    path.assign(boxes, torch.tensor([[0, 1]], dtype=torch.int32).cuda(), torch.tensor([2], dtype=torch.int32).cuda())
+    assert int(path.status.item()) & _lib.RN_FLAG_IOU_RANGE
+    with pytest.raises(AssertionError):
+        path.check_status()
