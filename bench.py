@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='multi-GPU statistics exchange: own kernel over NVLink peer memory, or NCCL')
+    ap.add_argument('--mode', default='train_step', choices=['train_step', 'infer'],
+                    help='infer: BASELINE config 4 (decode + top-k per level + per-class NMS only; not the headline metric)')
+    ap.add_argument('--topk', type=int, default=1000)
     ap.add_argument('--no-overlap', action='store_true', help='keep the detection tail on the main stream')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
     ap.add_argument('--opt', action='append', default=[], help='rn_set_option name=value (tuning knob)')
@@ -309,6 +312,31 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.mode == 'infer':
+        # BASELINE configs[3]: inference post-processing only (standalone select -> top-k -> NMS)
+        path.topk_per_level = args.topk
+        for _ in range(args.warmup):
+            path.detect(logits, regs)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            path.detect(logits, regs)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if rank == 0:
+            peak, _ = measured_peaks()
+            sel_bytes = batch * path.anchors * 4 * wl.num_classes
+            print(json.dumps({
+                'metric': 'images/sec (decode + score>0.5 + top-%d per level + per-class NMS IoU 0.5)' % args.topk,
+                'value': world * batch * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(wl, args, batch),
+                'alg_bytes_per_step': sel_bytes, 'frac_of_hbm_whole_step': sel_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
+                'detections': int(path.det_count.sum().item()), 'candidates': int(path.cand_count.sum().item())}))
+        return 0
 
     # per-kernel CUDA events (on the launching stream) for the roofline object
     stage_events = {k: [] for k in ('assign', 'cls_sums', 'cls_loss', 'huber', 'select', 'nms')}
