@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument('--cls-mode', default='focal')
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--logits-dtype', default='f32', choices=['f32', 'bf16'],
+                    help='bf16: extension (SURVEY 8f-3), NOT the headline metric, which stays float32')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'peer', 'nccl'],
                     help='multi-GPU statistics exchange: own kernel over NVLink peer memory, or NCCL')
     ap.add_argument('--mode', default='train_step', choices=['train_step', 'infer'],
@@ -306,6 +308,8 @@ def run_b200(args):
     gt_counts = torch.from_numpy(gt_counts_h).to(dev)
     path.assign(gt_boxes, gt_classes, gt_counts)
     logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=1000 + rank, device=dev)
+    if args.logits_dtype == 'bf16':
+        logits = logits.bfloat16()
     torch.cuda.synchronize()
 
     def barrier():
@@ -431,7 +435,8 @@ def run_b200(args):
         A = path.anchors
         C = wl.num_classes
         peak, peak_src = measured_peaks()
-        cls_bytes = batch * A * (8 * C + 4)          # read logits + write dlogits + read label
+        esz = 2 if args.logits_dtype == 'bf16' else 4
+        cls_bytes = batch * A * (2 * esz * C + 4)    # read logits + write dlogits + read label
         bytes_per_kernel = {
             'assign': batch * (24 * A + 20 * wl.max_gt),
             'cls_sums': batch * A * (4 * C + 4),
@@ -451,7 +456,8 @@ def run_b200(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.logits_dtype == 'f32' else 'f32 math on bf16 logits',
+            'data': 'synthetic',
             'config': workload_config(wl, args, batch),
             'clocks': clocks,
             'e2e': {'value': world * batch * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,

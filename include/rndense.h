@@ -115,6 +115,11 @@ typedef struct rn_maps {
 #define RN_CLS_BALANCED_BCE 3 /* mean(balanced BCE, axis=0)             losses.py:96-110,127   */
 #define RN_CLS_DICE_FLAG 16   /* + mean_C(dice(smooth=0, axis=0))       losses.py:50-60,130    */
 
+/* element type of the logits / dlogits maps of the classification-loss entry points */
+#define RN_DTYPE_F32 0
+#define RN_DTYPE_BF16 1  /* bfloat16 in and out (128-bit bf16x8 accesses), float32 math; fast kernel only:
+                            compact labels, C % 8 == 0, focal (focus 2) / BCE / balanced BCE without dice */
+
 /* layout of the double-precision statistics vector (device), length RN_STATS_HEADER + 3*C.
  * It is the ONLY data exchanged between GPUs (one all-reduce(sum) per phase). */
 #define RN_STATS_HEADER 8
@@ -220,8 +225,8 @@ RN_API int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps_t* 
  * d_stats[RN_STAT_CLS_SUM].  dlogits may be NULL maps (p[0]==NULL) for forward only. */
 RN_API int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
                                const rn_maps_t* label, int dense_labels, int mode, float focus,
-                               float alpha, float eps, const rn_maps_t* dlogits, double* d_stats,
-                               void* d_workspace, size_t workspace_bytes, void* stream);
+                               float alpha, float eps, const rn_maps_t* dlogits, int logits_dtype,
+                               double* d_stats, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* losses.regression_loss (losses.py:144-152): Huber(delta=1) on fg anchors, gradient
  * clip(e,-1,1)/(4 num_fg) (num_fg read from d_stats), WRITES d_stats[RN_STAT_HUBER_SUM].
@@ -335,7 +340,8 @@ RN_API int rn_select_finalize(const rn_pyramid_t* pyr, int batch, const rn_maps_
 RN_API int rn_fused_select_supported(int num_classes, int mode, float focus, const rn_rows_t* rows);
 RN_API int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
                               const rn_maps_t* label, int mode, float focus, float alpha, float eps,
-                              const rn_maps_t* dlogits, double* d_stats, void* d_loss_workspace,
+                              const rn_maps_t* dlogits, int logits_dtype, double* d_stats,
+                              void* d_loss_workspace,
                               size_t loss_workspace_bytes, float score_thr, int capacity,
                               int32_t* d_cand_count, uint32_t* d_status, void* d_select_workspace,
                               size_t select_workspace_bytes, void* stream);

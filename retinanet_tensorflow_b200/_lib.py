@@ -20,6 +20,7 @@ RN_LABEL_IGNORE = -2
 
 RN_CLS_NONE, RN_CLS_FOCAL, RN_CLS_BCE, RN_CLS_BALANCED_BCE = 0, 1, 2, 3
 RN_CLS_DICE_FLAG = 16
+RN_DTYPE_F32, RN_DTYPE_BF16 = 0, 1
 
 RN_STAT_TRAINABLE, RN_STAT_NUM_FG, RN_STAT_CLS_SUM, RN_STAT_HUBER_SUM = 0, 1, 2, 3
 
@@ -91,7 +92,7 @@ PROTOTYPES = {
     'rn_label_stats_dense': (_i, [_i64, _i, _vp, _vp, _vp]),
     'rn_loss_workspace_bytes': (_sz, [_i]),
     'rn_cls_sums': (_i, [_RP, _i, _MP, _MP, _i, _vp, _vp, _sz, _vp]),
-    'rn_cls_loss_fwd_bwd': (_i, [_RP, _i, _MP, _MP, _i, _i, _f, _f, _f, _MP, _vp, _vp, _sz, _vp]),
+    'rn_cls_loss_fwd_bwd': (_i, [_RP, _i, _MP, _MP, _i, _i, _f, _f, _f, _MP, _i, _vp, _vp, _sz, _vp]),
     'rn_huber_fwd_bwd': (_i, [_RP, _MP, _MP, _MP, _MP, _MP, _vp, _vp, _sz, _vp]),
     'rn_huber_rows': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_loss_finalize': (_i, [_i, _i, _vp, _vp, _vp]),
@@ -108,7 +109,7 @@ PROTOTYPES = {
     'rn_decode_select': (_i, [_PP, _i, _i, _MP, _i, _MP, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_select_finalize': (_i, [_PP, _i, _MP, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_fused_select_supported': (_i, [_i, _i, _f, _RP]),
-    'rn_cls_loss_select': (_i, [_RP, _i, _MP, _MP, _i, _f, _f, _f, _MP, _vp, _vp, _sz, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    'rn_cls_loss_select': (_i, [_RP, _i, _MP, _MP, _i, _f, _f, _f, _MP, _i, _vp, _vp, _sz, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     'rn_nms_workspace_bytes': (_sz, [_i, _i, _i]),
     'rn_nms_classwise': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

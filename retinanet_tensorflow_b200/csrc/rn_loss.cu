@@ -13,6 +13,8 @@
 
 #include <cmath>
 
+#include <cuda_bf16.h>
+
 #include "rn_common.cuh"
 
 namespace rn {
@@ -236,8 +238,9 @@ struct FocalFastParams {
   double* partials;
   unsigned* ticket;
   int num_classes;
-  int cv;           // float4 units per row
+  int cv;           // 16-byte units per row (C/4 float32, C/8 bfloat16)
   int write_grad;
+  int bf16;         // logits / dlogits are bfloat16
   // fused candidate pre-selection (rn_cls_loss_select): the same pass also finds the anchors whose
   // max class probability exceeds `thr` (utils.boxes_decode, utils.py:183-190)
   float sel_trigger;   // logit below which sigmoid(x) <= thr for sure
@@ -465,7 +468,26 @@ __device__ __forceinline__ void fast_bulk_unit(const FastCtx cx, unsigned c4, fl
 // gradient (z A_c + B_c) p (1-p).  Compact labels, C % 4 == 0.
 // FIXED_COL: the grid stride is a multiple of the row length, so a thread's float4 column never
 // changes and its row advances by a constant (no wrap test in the loop).
-template <int MODE, bool DICE, int MINB, bool SELECT, bool FIXED_COL>
+// BF16: logits and gradients are bfloat16 (a unit is 8 logits = one 128-bit access, "bf16x8"); the math
+// stays float32.  C % 8 == 0; not combined with DICE.
+__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float4& lo, float4& hi) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  const float2 c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+  lo = make_float4(a.x, a.y, b.x, b.y);
+  hi = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float4& lo, const float4& hi) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+  h[0] = __floats2bfloat162_rn(lo.x, lo.y);
+  h[1] = __floats2bfloat162_rn(lo.z, lo.w);
+  h[2] = __floats2bfloat162_rn(hi.x, hi.y);
+  h[3] = __floats2bfloat162_rn(hi.z, hi.w);
+  return r;
+}
+
+template <int MODE, bool DICE, int MINB, bool SELECT, bool FIXED_COL, bool BF16>
 __global__ void __launch_bounds__(kLossThreads, MINB)
 cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
   extern __shared__ __align__(16) float s_tab[];   // [4][C]: w_neg, w_pos, dice A, dice B (when needed)
@@ -510,20 +532,21 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ Focal
   const float trig = SELECT ? prm.sel_trigger : INFINITY;
   double acc_neg = 0.0, acc_pos = 0.0;
 
+  using Unit = uint4;   // 16 bytes: float4 (4 logits) or bf16x8 (8 logits)
+  constexpr unsigned kPerUnit = BF16 ? 8u : 4u;
   for (int s = 0; s < segs.num; ++s) {
     const unsigned units = (unsigned)segs.rows[s] * cv;   // < 2^32 - 2^24, checked by the host
-    const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
+    const Unit* __restrict__ xin = reinterpret_cast<const Unit*>(prm.logits.p[s]);
     const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
-    float4* __restrict__ gout = reinterpret_cast<float4*>(prm.dlogits.p[s]);
+    Unit* __restrict__ gout = reinterpret_cast<Unit*>(prm.dlogits.p[s]);
     unsigned u = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned row = u / cv;          // one division per thread per segment
     unsigned col = u - row * cv;
     float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);   // four short float accumulators
 
-    // one unit: classify, compute, store
-    auto do_unit = [&](unsigned uu, unsigned rr, unsigned cc, const float4& v, int lab) {
-      const unsigned c4 = cc * 4u;
-      float4 g, l;
+    // four logits of one row: classify, compute
+    auto do_quad = [&](unsigned rr, unsigned c4, const float4& v, int lab, float4& g) {
+      float4 l;
       const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
       const bool plain = xmax <= -0.70f && (unsigned)(lab - (int)c4) >= 4u;   // also true for IGNORE (< 0)
       if (plain && xmax <= trig) {
@@ -539,7 +562,22 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ Focal
         acc4.x += o.l.x; acc4.y += o.l.y; acc4.z += o.l.z; acc4.w += o.l.w;
         acc_pos += (double)o.pos;
       }
-      if (write_grad) __stcs(gout + uu, g);
+    };
+    // one 16-byte unit
+    auto do_unit = [&](unsigned uu, unsigned rr, unsigned cc, const Unit& raw, int lab) {
+      Unit out;
+      if constexpr (BF16) {
+        float4 lo, hi, glo, ghi;
+        unpack_bf16x8(raw, lo, hi);
+        do_quad(rr, cc * 8u, lo, lab, glo);
+        do_quad(rr, cc * 8u + 4u, hi, lab, ghi);
+        out = pack_bf16x8(glo, ghi);
+      } else {
+        float4 g;
+        do_quad(rr, cc * 4u, *reinterpret_cast<const float4*>(&raw), lab, g);
+        out = *reinterpret_cast<const Unit*>(&g);
+      }
+      if (write_grad) __stcs(gout + uu, out);
     };
 
     // main loop: four units per iteration, all loads first, no bounds tests
@@ -554,10 +592,10 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ Focal
         c2 = c1 + dcol;  r2 = r1 + drow;  if (c2 >= cv) { c2 -= cv; r2 += 1; }
         c3 = c2 + dcol;  r3 = r2 + drow;  if (c3 >= cv) { c3 -= cv; r3 += 1; }
       }
-      const float4 v0 = __ldcs(xin + u);
-      const float4 v1 = __ldcs(xin + u + gstride);
-      const float4 v2 = __ldcs(xin + u + 2u * gstride);
-      const float4 v3 = __ldcs(xin + u + 3u * gstride);
+      const Unit v0 = __ldcs(xin + u);
+      const Unit v1 = __ldcs(xin + u + gstride);
+      const Unit v2 = __ldcs(xin + u + 2u * gstride);
+      const Unit v3 = __ldcs(xin + u + 3u * gstride);
       const int l0 = __ldg(lab_p + row);
       const int l1 = __ldg(lab_p + r1);
       const int l2 = __ldg(lab_p + r2);
@@ -575,7 +613,7 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ Focal
     }
     // tail: at most three units
     for (; u < units; u += gstride) {
-      const float4 v = __ldcs(xin + u);
+      const Unit v = __ldcs(xin + u);
       const int lab = __ldg(lab_p + row);
       do_unit(u, row, col, v, lab);
       col += dcol;
@@ -585,6 +623,7 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ Focal
         row += 1;
       }
     }
+    (void)kPerUnit;
     acc_neg += ((double)acc4.x + (double)acc4.y) + ((double)acc4.z + (double)acc4.w);
   }
   // focal: negatives accumulated w^2 log(q+eps), loss = -(1-alpha) * that; BCE modes: plain sum
@@ -1092,7 +1131,7 @@ static unsigned gcd_u(unsigned a, unsigned b) {
   return a;
 }
 
-template <int MODE, bool DICE>
+template <int MODE, bool DICE, bool BF16>
 static void launch_fast_variant(const Segs& segs, const FocalFastParams& fp, bool select, long long work,
                                 size_t smem, cudaStream_t st) {
   // 4 resident CTAs of 256 threads per SM (64 registers): measured faster than 5 x 48 registers.
@@ -1100,13 +1139,13 @@ static void launch_fast_variant(const Segs& segs, const FocalFastParams& fp, boo
   // < 4 % of the CTAs, which makes every thread's float4 column constant (FIXED_COL).
 #define RN_LAUNCH_FF(SEL)                                                                                       \
   do {                                                                                                          \
-    unsigned g = persistent_grid(cls_fast_kernel<MODE, DICE, 4, SEL, false>, kLossThreads, smem, work);         \
+    unsigned g = persistent_grid(cls_fast_kernel<MODE, DICE, 4, SEL, false, BF16>, kLossThreads, smem, work);   \
     const unsigned q = (unsigned)fp.cv / gcd_u((unsigned)fp.cv, (unsigned)kLossThreads);                        \
     const unsigned gf = g / q * q;                                                                              \
     if (gf > 0 && (g - gf) * 25u <= g) {                                                                        \
-      cls_fast_kernel<MODE, DICE, 4, SEL, true><<<gf, kLossThreads, smem, st>>>(segs, fp);                      \
+      cls_fast_kernel<MODE, DICE, 4, SEL, true, BF16><<<gf, kLossThreads, smem, st>>>(segs, fp);                \
     } else {                                                                                                    \
-      cls_fast_kernel<MODE, DICE, 4, SEL, false><<<g, kLossThreads, smem, st>>>(segs, fp);                      \
+      cls_fast_kernel<MODE, DICE, 4, SEL, false, BF16><<<g, kLossThreads, smem, st>>>(segs, fp);                \
     }                                                                                                           \
   } while (0)
   if (select) RN_LAUNCH_FF(true); else RN_LAUNCH_FF(false);
@@ -1119,22 +1158,30 @@ static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, int mo
   const int base = mode & 15;
   const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
   const size_t smem = (dice || base == RN_CLS_BALANCED_BCE) ? 4 * (size_t)fp.num_classes * sizeof(float) : 0;
-  switch (base) {
-    case RN_CLS_FOCAL:
-      if (dice) launch_fast_variant<RN_CLS_FOCAL, true>(segs, fp, select, work, smem, st);
-      else launch_fast_variant<RN_CLS_FOCAL, false>(segs, fp, select, work, smem, st);
-      break;
-    case RN_CLS_BCE:
-      if (dice) launch_fast_variant<RN_CLS_BCE, true>(segs, fp, select, work, smem, st);
-      else launch_fast_variant<RN_CLS_BCE, false>(segs, fp, select, work, smem, st);
-      break;
-    case RN_CLS_BALANCED_BCE:
-      if (dice) launch_fast_variant<RN_CLS_BALANCED_BCE, true>(segs, fp, select, work, smem, st);
-      else launch_fast_variant<RN_CLS_BALANCED_BCE, false>(segs, fp, select, work, smem, st);
-      break;
-    default:
-      launch_fast_variant<RN_CLS_NONE, true>(segs, fp, select, work, smem, st);
-      break;
+  if (fp.bf16) {   // bf16x8 units; not combined with dice (checked by the callers)
+    switch (base) {
+      case RN_CLS_FOCAL: launch_fast_variant<RN_CLS_FOCAL, false, true>(segs, fp, select, work, smem, st); break;
+      case RN_CLS_BCE: launch_fast_variant<RN_CLS_BCE, false, true>(segs, fp, select, work, smem, st); break;
+      default: launch_fast_variant<RN_CLS_BALANCED_BCE, false, true>(segs, fp, select, work, smem, st); break;
+    }
+  } else {
+    switch (base) {
+      case RN_CLS_FOCAL:
+        if (dice) launch_fast_variant<RN_CLS_FOCAL, true, false>(segs, fp, select, work, smem, st);
+        else launch_fast_variant<RN_CLS_FOCAL, false, false>(segs, fp, select, work, smem, st);
+        break;
+      case RN_CLS_BCE:
+        if (dice) launch_fast_variant<RN_CLS_BCE, true, false>(segs, fp, select, work, smem, st);
+        else launch_fast_variant<RN_CLS_BCE, false, false>(segs, fp, select, work, smem, st);
+        break;
+      case RN_CLS_BALANCED_BCE:
+        if (dice) launch_fast_variant<RN_CLS_BALANCED_BCE, true, false>(segs, fp, select, work, smem, st);
+        else launch_fast_variant<RN_CLS_BALANCED_BCE, false, false>(segs, fp, select, work, smem, st);
+        break;
+      default:
+        launch_fast_variant<RN_CLS_NONE, true, false>(segs, fp, select, work, smem, st);
+        break;
+    }
   }
   RN_CUDA_CHECK_LAUNCH("fast classification-loss kernel");
   return RN_OK;
@@ -1234,8 +1281,8 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
 
 extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
                                    const rn_maps_t* label, int dense_labels, int mode, float focus, float alpha,
-                                   float eps, const rn_maps_t* dlogits, double* d_stats, void* d_workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   float eps, const rn_maps_t* dlogits, int logits_dtype, double* d_stats,
+                                   void* d_workspace, size_t workspace_bytes, void* stream) {
   int rc = check_rows(rows, "rn_cls_loss_fwd_bwd");
   if (rc) return rc;
   RN_REQUIRE(maps_present(logits) && maps_present(label) && d_stats && d_workspace, RN_ERR_BAD_ARG,
@@ -1275,10 +1322,17 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   RN_REQUIRE(smem <= 48 * 1024, RN_ERR_UNSUPPORTED, "rn_cls_loss_fwd_bwd: too many classes");
   cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
   const bool dense = dense_labels != 0;
+  RN_REQUIRE(logits_dtype == RN_DTYPE_F32 || logits_dtype == RN_DTYPE_BF16, RN_ERR_BAD_ARG, "unknown logits_dtype");
+  const bool bf16 = logits_dtype == RN_DTYPE_BF16;
   bool fits32 = true;  // the fast kernel indexes float4 units with 32-bit integers
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
-  if ((base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_focal && fits32 && num_classes <= 2048) {
+  const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_focal && fits32 &&
+                       num_classes <= 2048;
+  RN_REQUIRE(!bf16 || (fast_ok && !dice && base != RN_CLS_NONE && num_classes % 8 == 0), RN_ERR_UNSUPPORTED,
+             "bfloat16 logits need the fast kernel: compact labels, C %% 8 == 0, focal (focus 2) / BCE / balanced BCE "
+             "without dice");
+  if (fast_ok) {
     FocalFastParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.logits = prm.logits;
@@ -1291,9 +1345,10 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     fp.partials = prm.partials;
     fp.ticket = prm.ticket;
     fp.num_classes = num_classes;
-    fp.cv = num_classes / 4;
+    fp.cv = num_classes / (bf16 ? 8 : 4);
+    fp.bf16 = bf16 ? 1 : 0;
     fp.write_grad = prm.write_grad;
-    return launch_focal_fast(segs, fp, mode, false, units, st);
+    return launch_focal_fast(segs, fp, mode, false, segs.start[RN_MAX_LEVELS] * (long long)fp.cv, st);
   }
   switch (base) {
     case RN_CLS_FOCAL:
@@ -1328,7 +1383,7 @@ extern "C" int rn_fused_select_supported(int num_classes, int mode, float focus,
 
 extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
                                   const rn_maps_t* label, int mode, float focus, float alpha, float eps,
-                                  const rn_maps_t* dlogits, double* d_stats, void* d_loss_workspace,
+                                  const rn_maps_t* dlogits, int logits_dtype, double* d_stats, void* d_loss_workspace,
                                   size_t loss_workspace_bytes, float score_thr, int capacity, int32_t* d_cand_count,
                                   uint32_t* d_status, void* d_select_workspace, size_t select_workspace_bytes,
                                   void* stream) {
@@ -1364,8 +1419,13 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
   fp.stats_out = d_stats;
   fp.ticket = reinterpret_cast<unsigned*>(d_loss_workspace);
   fp.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_loss_workspace) + 256);
+  RN_REQUIRE(logits_dtype == RN_DTYPE_F32 || logits_dtype == RN_DTYPE_BF16, RN_ERR_BAD_ARG, "unknown logits_dtype");
+  const bool bf16 = logits_dtype == RN_DTYPE_BF16;
+  RN_REQUIRE(!bf16 || (num_classes % 8 == 0 && !(mode & RN_CLS_DICE_FLAG) && (mode & 15) != RN_CLS_NONE),
+             RN_ERR_UNSUPPORTED, "bfloat16 logits need C %% 8 == 0 and a mode without dice");
   fp.num_classes = num_classes;
-  fp.cv = num_classes / 4;
+  fp.cv = num_classes / (bf16 ? 8 : 4);
+  fp.bf16 = bf16 ? 1 : 0;
   fp.write_grad = grad ? 1 : 0;
   // sigmoid(x) > thr needs x > logit(thr); leave a margin for the float32 sigmoid's rounding
   const double lg = std::log((double)score_thr / (1.0 - (double)score_thr));

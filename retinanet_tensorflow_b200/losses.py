@@ -200,7 +200,7 @@ class _ClassificationLoss(torch.autograd.Function):
             seg = _lib.rows_of([rows])
             _lib.call('rn_cls_loss_fwd_bwd', C.byref(seg), c, C.byref(_lib.maps_of([logits.reshape(rows, c)])),
                       C.byref(_lib.maps_of([labels.reshape(rows, c)])), 1, code, 2.0, 0.25, 1e-7,
-                      C.byref(_lib.maps_of([grad.reshape(rows, c)])), _lib.ptr(stats), _lib.ptr(ws), n,
+                      C.byref(_lib.maps_of([grad.reshape(rows, c)])), _lib.RN_DTYPE_F32, _lib.ptr(stats), _lib.ptr(ws), n,
                       _lib.stream_ptr())
         _lib.call('rn_loss_finalize', c, code, _lib.ptr(stats), _lib.ptr(out), _lib.stream_ptr())
         ctx.save_for_backward(grad)

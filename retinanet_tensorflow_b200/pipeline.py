@@ -132,7 +132,7 @@ class DenseHeadPath(object):
                       C.byref(m))
         return m
 
-    def _maps(self, x, trailing):
+    def _maps(self, x, trailing, dtypes=(torch.float32,)):
         """rn_maps_t for a merged tensor [R, trailing] or a list/dict of per-level tensors."""
         if isinstance(x, dict):
             x = [x[n] for n in self.names]
@@ -141,16 +141,32 @@ class DenseHeadPath(object):
             if len(x) != len(shapes):
                 raise ValueError('expected %d levels' % len(shapes))
             for t, (h, w, a) in zip(x, shapes):
-                if tuple(t.shape) != (self.batch, h, w, a, trailing) or t.dtype != torch.float32:
-                    raise ValueError('level tensor must be float32 [%d,%d,%d,%d,%d], got %s %s'
-                                     % (self.batch, h, w, a, trailing, tuple(t.shape), t.dtype))
+                if tuple(t.shape) != (self.batch, h, w, a, trailing) or t.dtype not in dtypes or t.dtype != x[0].dtype:
+                    raise ValueError('level tensor must be %s [%d,%d,%d,%d,%d], got %s %s'
+                                     % (dtypes, self.batch, h, w, a, trailing, tuple(t.shape), t.dtype))
             ts = [t.contiguous() for t in x]
             return _lib.maps_of(ts), ts
-        if tuple(x.shape) != (self.rows_total, trailing) or x.dtype != torch.float32:
-            raise ValueError('merged tensor must be float32 [%d,%d], got %s %s'
-                             % (self.rows_total, trailing, tuple(x.shape), x.dtype))
+        if tuple(x.shape) != (self.rows_total, trailing) or x.dtype not in dtypes:
+            raise ValueError('merged tensor must be %s [%d,%d], got %s %s'
+                             % (dtypes, self.rows_total, trailing, tuple(x.shape), x.dtype))
         x = x.contiguous()
-        return self._merged_maps(x, 4 * trailing), x
+        return self._merged_maps(x, x.element_size() * trailing), x
+
+    _LOGIT_DTYPES = (torch.float32, torch.bfloat16)
+
+    def _grad_buffers(self, logits_t, want_grad):
+        """(dlogits maps, dreg maps, logits dtype code); dlogits follows the logits' dtype."""
+        first = logits_t[0] if isinstance(logits_t, (list, tuple)) else logits_t
+        code = _lib.RN_DTYPE_BF16 if first.dtype == torch.bfloat16 else _lib.RN_DTYPE_F32
+        if not want_grad:
+            return _lib.Maps(), _lib.Maps(), code
+        Cn = self.num_classes
+        if self.dlogits is None or self.dlogits.dtype != first.dtype:
+            self.dlogits = torch.empty((self.rows_total, Cn), dtype=first.dtype, device=self.device)
+        if self.dreg is None:
+            self.dreg = torch.empty((self.rows_total, 4), dtype=torch.float32, device=self.device)
+        return (self._merged_maps(self.dlogits, self.dlogits.element_size() * Cn), self._merged_maps(self.dreg, 16),
+                code)
 
     def per_level(self, merged, trailing=()):
         """Reference-shaped views `[B, H, W, A, ...]` keyed 'P3'.. of a merged buffer."""
@@ -214,18 +230,11 @@ class DenseHeadPath(object):
     def loss(self, logits, regression, want_grad=True):
         """Returns self.loss_out (device f32 [4]: class loss, regression loss, num_fg, M); the
         gradients w.r.t. the full logits / regression maps land in self.dlogits / self.dreg."""
-        m_logits, _ = self._maps(logits, self.num_classes)
+        m_logits, logits_t = self._maps(logits, self.num_classes, self._LOGIT_DTYPES)
         m_reg, _ = self._maps(regression, 4)
         st = _lib.stream_ptr()
         Cn = self.num_classes
-        if want_grad:
-            if self.dlogits is None:
-                self.dlogits = torch.empty((self.rows_total, Cn), dtype=torch.float32, device=self.device)
-                self.dreg = torch.empty((self.rows_total, 4), dtype=torch.float32, device=self.device)
-            m_dlogits = self._merged_maps(self.dlogits, 4 * Cn)
-            m_dreg = self._merged_maps(self.dreg, 16)
-        else:
-            m_dlogits, m_dreg = _lib.Maps(), _lib.Maps()
+        m_dlogits, m_dreg, dt = self._grad_buffers(logits_t, want_grad)
         if self.mode & _lib.RN_CLS_DICE_FLAG:
             self._stage('cls_sums', lambda: _lib.call(
                 'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
@@ -233,7 +242,7 @@ class DenseHeadPath(object):
             self._allreduce('dice_sums')
         self._stage('cls_loss', lambda: _lib.call(
             'rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, self.mode,
-            self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
+            self.focus, self.alpha, self.eps, C.byref(m_dlogits), dt, _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
             self._loss_ws_bytes, st))
         self._stage('huber', lambda: _lib.call(
             'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
@@ -257,18 +266,11 @@ class DenseHeadPath(object):
             self.loss(logits, regression, want_grad)
             self.select(logits, regression)
             return self.loss_out, self.cand_count
-        m_logits, _ = self._maps(logits, self.num_classes)
+        m_logits, logits_t = self._maps(logits, self.num_classes, self._LOGIT_DTYPES)
         m_reg, _ = self._maps(regression, 4)
         st = _lib.stream_ptr()
         Cn = self.num_classes
-        if want_grad:
-            if self.dlogits is None:
-                self.dlogits = torch.empty((self.rows_total, Cn), dtype=torch.float32, device=self.device)
-                self.dreg = torch.empty((self.rows_total, 4), dtype=torch.float32, device=self.device)
-            m_dlogits = self._merged_maps(self.dlogits, 4 * Cn)
-            m_dreg = self._merged_maps(self.dreg, 16)
-        else:
-            m_dlogits, m_dreg = _lib.Maps(), _lib.Maps()
+        m_dlogits, m_dreg, dt = self._grad_buffers(logits_t, want_grad)
         if self.mode & _lib.RN_CLS_DICE_FLAG:
             self._stage('cls_sums', lambda: _lib.call(
                 'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
@@ -276,7 +278,7 @@ class DenseHeadPath(object):
             self._allreduce('dice_sums')
         self._stage('cls_loss', lambda: _lib.call(
             'rn_cls_loss_select', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode,
-            self.focus, self.alpha, self.eps, C.byref(m_dlogits), _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
+            self.focus, self.alpha, self.eps, C.byref(m_dlogits), dt, _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
             self._loss_ws_bytes, self.score_thr, self.capacity, _lib.ptr(self.cand_count), _lib.ptr(self.status),
             _lib.ptr(self._sel_ws), self._sel_ws_bytes, st))
         self._stage('huber', lambda: _lib.call(
@@ -301,6 +303,8 @@ class DenseHeadPath(object):
 
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
+        if isinstance(scores, torch.Tensor) and scores.dtype == torch.bfloat16:
+            scores = scores.float()   # the standalone select kernel is float32; bf16 is fused-path only
         m_scores, _ = self._maps(scores, self.num_classes)
         m_reg, _ = self._maps(regression, 4)
         self._stage('select', lambda: _lib.call(

@@ -96,7 +96,7 @@ def test_argument_validation_status_codes():
         _lib.call('rn_anchor_generate', None, None, None, None)
     # NULL inputs are rejected before any launch (no GPU needed to get the error)
     rows = _lib.rows_of([4])
-    assert _lib.lib.rn_cls_loss_fwd_bwd(C.byref(rows), 3, None, None, 0, 1, 2.0, 0.25, 1e-7, None, None, None, 0,
+    assert _lib.lib.rn_cls_loss_fwd_bwd(C.byref(rows), 3, None, None, 0, 1, 2.0, 0.25, 1e-7, None, 0, None, None, 0,
                                         None) == -1
     assert _lib.lib.rn_nms_classwise(1, 1, 8, None, None, None, None, 0.5, 10, 8, None, None, None, None, None, None,
                                      None, 0, None) == -1

@@ -147,3 +147,51 @@ def test_reference_huber_vector():
     _lib.call('rn_loss_finalize', 1, _lib.RN_CLS_BCE, _lib.ptr(stats), _lib.ptr(out), _lib.stream_ptr())
     assert out[1].item() == 2.0
     np.testing.assert_array_equal(dpred.cpu().numpy(), np.array([[-1.] * 4, [0.] * 4, [-1.] * 4]) / 8.0)
+
+
+@pytest.mark.parametrize('mode', ['focal', 'bce', 'balanced_bce'])
+def test_bf16_logits_in_and_out(mode):
+    """bfloat16 logits (bf16x8 accesses) through the fast kernel: float32 math on the upcast values,
+    so the loss equals the oracle's on logits.bfloat16().float() and the bf16 gradient equals the
+    oracle's gradient rounded to bf16 (up to one bf16 ulp)."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['voc']          # C = 20 is not a multiple of 8 -> use a 24-class variant
+    wl = synthetic.Workload('voc24', wl.config, wl.image_h, wl.image_w, 24, wl.max_gt, 2)
+    ref = helpers.oracle_labels_batch(wl, 2)
+    cls = helpers.merge_levels(ref['cls'], 1)
+    mask = helpers.merge_levels(ref['mask'])
+    reg = helpers.merge_levels(ref['reg'], 1)
+    lab = helpers.compact_labels(cls, mask)
+    logits, regs = synthetic.head_outputs(lab, reg, wl.num_classes, seed=21, device='cpu')
+    logits16 = logits.bfloat16()
+    boxes, classes, counts = synthetic.gt_batch(wl, 2)
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 2, wl.max_gt, cls_mode=mode, capacity=8192,
+                         process_group=False)
+    gt = [torch.from_numpy(x).cuda() for x in (boxes, classes, counts)]
+    path.step(*gt, logits16.cuda(), regs.cuda())
+    torch.cuda.synchronize()
+    assert path.dlogits.dtype == torch.bfloat16
+    x = logits16.float().numpy()
+    r = regs.numpy()
+    labels = oracle.Detection(oracle.Classification(None, cls[mask]), reg[mask], None)
+    preds = oracle.Detection(oracle.Classification(x[mask], oracle.sigmoid(x[mask])), r[mask], None)
+    cl, rl = oracle.loss(labels, preds, mode=mode)
+    out = path.loss_out.cpu().numpy()
+    np.testing.assert_allclose(out[:2], [cl, rl], rtol=1e-5)
+    fg = oracle.classmap_decode(cls[mask]).fg_mask
+    g_ref = np.zeros_like(x)
+    g_ref[mask] = oracle.classification_loss_grad(cls[mask], x[mask], fg, mode=mode)
+    got = path.dlogits.float().cpu().numpy()
+    helpers.assert_close(got, g_ref, rtol=2.0 ** -7, atol=1e-6 * np.abs(g_ref).max(), what='bf16 dlogits ' + mode)
+    # detections equal the float32 path's on the same (upcast) logits
+    ref_path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 2, wl.max_gt, cls_mode=mode, capacity=8192,
+                             process_group=False)
+    ref_path.step(*gt, logits16.float().cuda(), regs.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(ref_path.det_count, path.det_count) and torch.equal(ref_path.loss_out, path.loss_out)
+    for b in range(2):
+        m = int(path.det_count[b])
+        assert torch.equal(ref_path.det_index[b, :m], path.det_index[b, :m])
+        assert torch.equal(ref_path.det_boxes[b, :m], path.det_boxes[b, :m])
