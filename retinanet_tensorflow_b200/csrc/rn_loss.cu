@@ -9,6 +9,15 @@
 // and the multi-GPU exchange is one all-reduce of that vector.  Loss sums are reduced
 // warp -> block -> (per-block partials, fixed-order final pass by the last block), so results
 // are run-to-run deterministic.
+//
+// Layout of this file:
+//   cls_loss_kernel       generic kernel (any mode, dense or compact labels, any C, any focus):
+//                         libm + IEEE division, ~110 instructions per logit -- the fallback
+//   cls_fast_kernel       the product path for compact labels and C % 4 == 0 (focal with focus 2,
+//                         BCE, balanced BCE, +-dice, float32 or bf16x8): ~34 instructions per logit,
+//                         optional fused candidate pre-selection (rn_cls_loss_select)
+//   cls_sums_*            dice phase 1 (per-class sums), huber_*, loss_finalize, elementwise /
+//                         column-sum / softmax forms for the reference's own signatures
 #include <string.h>
 
 #include <cmath>
@@ -210,17 +219,16 @@ cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsPa
   }
 }
 
-// ---- fast path: focal (focus == 2), compact labels, C % 4 == 0 -------------------------------------
+// ---- fast path: compact labels, C % 4 == 0 ------------------------------------------------------------
 // The generic kernel above spends ~110 instructions per logit (IEEE divisions, libm expf/logf with
 // their special-case branches, a 64-bit division per unit) and is issue-bound at a third of the
-// HBM roofline.  This kernel keeps the reference's op sequence (p, naive 1-p, eps inside the log)
-// but evaluates each primitive with the cheapest form that stays within ~1 ulp:
-//   exp  : ex2.approx on a hi/lo-split x*log2(e)            (rel. err <= 2.4e-7)
-//   1/d  : rcp.approx + one Newton step                      (<= 1 ulp)
-//   log  : exponent/mantissa split + degree-9 minimax log1p  (rel. err <= 1.2e-7, no branches)
+// HBM roofline.  The fast kernel keeps the reference's op sequence (p, naive 1-p, eps inside the
+// log) but evaluates each primitive with the cheapest form that stays within ~1 ulp:
+//   exp  : ex2.approx (on an exactly split x*log2(e) where p -> 1 matters)   (rel. err <= 2.4e-7)
+//   1/d  : rcp.approx (+ one Newton step where p -> 1 matters)               (<= 1 ulp)
+//   log  : exponent/mantissa split + minimax log1p, no branches              (rel. err <= 1.2e-7)
 // and treats every element as a negative (z = 0); the at-most-one positive element of a row is
-// recomputed afterwards on a rare path.  Row/column of a unit advance incrementally, so the
-// loop has no division.
+// recomputed on a rare path.  See DESIGN.md section 4 for the loop structure and its history.
 // exp(-x), clamped so that 1 + e stays finite.  The product x*log2(e) is split into its rounded
 // value and its exact rounding error (one FFMA), so the result carries only ex2.approx's error.
 __device__ __forceinline__ float exp_neg_fast(float x) {
@@ -230,7 +238,7 @@ __device__ __forceinline__ float exp_neg_fast(float x) {
   const float e = ex2_approx(fminf(t, 126.0f));
   return fmaf(e * r, 0.693147182f, e);
 }
-struct FocalFastParams {
+struct FastParams {
   Ptrs logits, label, dlogits;
   float alpha, eps;
   const double* stats;
@@ -328,7 +336,7 @@ struct UnitOut {
 };
 
 template <int MODE, bool DICE, bool SELECT>
-__device__ __noinline__ UnitOut fast_slow_unit(FastCtx cx, const FocalFastParams& prm, const Segs& segs, int s,
+__device__ __noinline__ UnitOut fast_slow_unit(FastCtx cx, const FastParams& prm, const Segs& segs, int s,
                                                unsigned row, unsigned c4, int lab, float4 v) {
   UnitOut out;
   out.pos = 0.f;
@@ -489,7 +497,7 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float4& lo, const float4& hi)
 
 template <int MODE, bool DICE, int MINB, bool SELECT, bool FIXED_COL, bool BF16>
 __global__ void __launch_bounds__(kLossThreads, MINB)
-cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FocalFastParams prm) {
+cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastParams prm) {
   extern __shared__ __align__(16) float s_tab[];   // [4][C]: w_neg, w_pos, dice A, dice B (when needed)
   __shared__ double s_red[32];
   constexpr bool kTables = DICE || MODE == RN_CLS_BALANCED_BCE;
@@ -1070,7 +1078,7 @@ __global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float*
 }
 
 // rn_set_option("fast_focal", 0) forces the generic kernel (used by the parity tests to cover both)
-static int g_fast_focal = 1;
+static int g_fast_kernels = 1;
 
 // Persistent grid: exactly the number of CTAs that are resident at once (one full wave), so a
 // grid-stride loop never runs a partially filled second wave.
@@ -1087,7 +1095,7 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem, long long wo
   return (unsigned)blocks;
 }
 
-static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, int mode, bool select, long long units,
+static int launch_fast(const Segs& segs, const FastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st);
 
 static unsigned loss_grid(long long units, int threads, int per_sm) {
@@ -1132,7 +1140,7 @@ static unsigned gcd_u(unsigned a, unsigned b) {
 }
 
 template <int MODE, bool DICE, bool BF16>
-static void launch_fast_variant(const Segs& segs, const FocalFastParams& fp, bool select, long long work,
+static void launch_fast_variant(const Segs& segs, const FastParams& fp, bool select, long long work,
                                 size_t smem, cudaStream_t st) {
   // 4 resident CTAs of 256 threads per SM (64 registers): measured faster than 5 x 48 registers.
   // The grid is the resident wave, rounded down to a multiple of cv / gcd(cv, 256) when that costs
@@ -1152,7 +1160,7 @@ static void launch_fast_variant(const Segs& segs, const FocalFastParams& fp, boo
 #undef RN_LAUNCH_FF
 }
 
-static int launch_focal_fast(const Segs& segs, const FocalFastParams& fp, int mode, bool select, long long units,
+static int launch_fast(const Segs& segs, const FastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st) {
   const long long work = (units + 3) / 4;
   const int base = mode & 15;
@@ -1194,7 +1202,7 @@ using namespace rn;
 extern "C" int rn_set_option(const char* name, int value) {
   RN_REQUIRE(name, RN_ERR_BAD_ARG, "rn_set_option: NULL name");
   if (strcmp(name, "fast_focal") == 0) {
-    g_fast_focal = value != 0;
+    g_fast_kernels = value != 0;
     return RN_OK;
   }
   rn::set_error("rn_set_option: unknown option '%s'", name);
@@ -1245,7 +1253,7 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   bool rows32 = true;
   for (int i = 0; i < rows->num_segments; ++i)
     if (rows->rows[i] >= (1ll << 31) - (1ll << 26)) rows32 = false;
-  if (!dense_labels && vec4 && g_fast_focal && rows32 && prm.cv <= 256) {
+  if (!dense_labels && vec4 && g_fast_kernels && rows32 && prm.cv <= 256) {
     prm.ry = 256 / prm.cv > 0 ? 256 / prm.cv : 1;
     const int fthreads = prm.cv * prm.ry;
     const size_t fsmem = (size_t)prm.ry * 2 * num_classes * sizeof(double);
@@ -1327,13 +1335,13 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   bool fits32 = true;  // the fast kernel indexes float4 units with 32-bit integers
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
-  const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_focal && fits32 &&
+  const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_kernels && fits32 &&
                        num_classes <= 2048;
   RN_REQUIRE(!bf16 || (fast_ok && !dice && base != RN_CLS_NONE && num_classes % 8 == 0), RN_ERR_UNSUPPORTED,
              "bfloat16 logits need the fast kernel: compact labels, C %% 8 == 0, focal (focus 2) / BCE / balanced BCE "
              "without dice");
   if (fast_ok) {
-    FocalFastParams fp;
+    FastParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.logits = prm.logits;
     fp.label = prm.label;
@@ -1348,7 +1356,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     fp.cv = num_classes / (bf16 ? 8 : 4);
     fp.bf16 = bf16 ? 1 : 0;
     fp.write_grad = prm.write_grad;
-    return launch_focal_fast(segs, fp, mode, false, segs.start[RN_MAX_LEVELS] * (long long)fp.cv, st);
+    return launch_fast(segs, fp, mode, false, segs.start[RN_MAX_LEVELS] * (long long)fp.cv, st);
   }
   switch (base) {
     case RN_CLS_FOCAL:
@@ -1374,7 +1382,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
 extern "C" int rn_fused_select_supported(int num_classes, int mode, float focus, const rn_rows_t* rows) {
   const int base = mode & 15;
   if (!rows || num_classes % 4 != 0 || num_classes > 2048 || (base == RN_CLS_FOCAL && focus != 2.0f) ||
-      (base == RN_CLS_NONE && !(mode & RN_CLS_DICE_FLAG)) || !g_fast_focal)
+      (base == RN_CLS_NONE && !(mode & RN_CLS_DICE_FLAG)) || !g_fast_kernels)
     return 0;
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4) + (1ull << 24) >= (1ull << 32)) return 0;
@@ -1408,7 +1416,7 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
     RN_REQUIRE(rows->rows[i] % rows->images == 0, RN_ERR_BAD_SHAPE, "rows[%d] is not a multiple of images", i);
   const Segs segs = make_segs(rows);
   cudaStream_t st = (cudaStream_t)stream;
-  FocalFastParams fp;
+  FastParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.logits = make_ptrs(logits);
   fp.label = make_ptrs(label);
@@ -1444,7 +1452,7 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
   cudaMemsetAsync(fp.ticket, 0, sizeof(unsigned), st);
   cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * rows->images, st);
   const long long units = segs.start[RN_MAX_LEVELS] * (long long)fp.cv;
-  return launch_focal_fast(segs, fp, mode, true, units, st);
+  return launch_fast(segs, fp, mode, true, units, st);
 }
 
 extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const rn_maps_t* target,
