@@ -834,6 +834,107 @@ __global__ void __launch_bounds__(512) cls_sums_fast_kernel(const __grid_constan
   }
 }
 
+// Flat variant (the one the pipeline uses): same streaming skeleton as cls_fast_kernel.  The grid
+// stride is a multiple of the row length, so a thread's float4 column -- its four classes -- is
+// constant and the per-class sums live in registers for the whole kernel; four units per
+// iteration with all loads first.  The in-block reduction is ordered (thread order), so the result
+// is run-to-run deterministic.
+__global__ void __launch_bounds__(kLossThreads, 4)
+cls_sums_flat_kernel(const __grid_constant__ Segs segs, const __grid_constant__ SumsParams prm) {
+  extern __shared__ double s_part[];   // [blockDim][8]: I[4], P[4] of every thread
+  const int C = prm.num_classes;
+  const unsigned cv = (unsigned)prm.cv;
+  const unsigned gstride = gridDim.x * blockDim.x;   // multiple of cv (host)
+  const unsigned drow = gstride / cv;
+  const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned col = gtid % cv;
+  const int c4 = (int)col * 4;
+  double ai[4] = {0, 0, 0, 0}, ap[4] = {0, 0, 0, 0};
+
+  auto prob = [](float x) {
+    if (x <= -0.70f) {  // same bulk formula as cls_fast_kernel: p = e / (1 + e), e = exp(x)
+      const float e = ex2_approx(x * 1.44269502163e+00f);
+      return e * rcp_approx(1.0f + e);
+    }
+    return sigmoid_f32(x);
+  };
+
+  for (int s = 0; s < segs.num; ++s) {
+    const unsigned units = (unsigned)segs.rows[s] * cv;
+    const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
+    const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
+    unsigned u = gtid;
+    unsigned row = u / cv;
+    float fp0 = 0.f, fp1 = 0.f, fp2 = 0.f, fp3 = 0.f;   // float partials of sum p, flushed per iteration
+
+    auto do_unit = [&](const float4& v, int lab) {
+      if (lab == RN_LABEL_IGNORE) return;
+      const float p0 = prob(v.x), p1 = prob(v.y), p2 = prob(v.z), p3 = prob(v.w);
+      fp0 += p0; fp1 += p1; fp2 += p2; fp3 += p3;
+      const unsigned d = (unsigned)(lab - c4);
+      if (d < 4u) {  // the row's positive class is one of mine (rare)
+        if (d == 0) ai[0] += (double)p0;
+        else if (d == 1) ai[1] += (double)p1;
+        else if (d == 2) ai[2] += (double)p2;
+        else ai[3] += (double)p3;
+      }
+    };
+
+    while (u + 3u * gstride < units) {
+      const float4 v0 = __ldcs(xin + u);
+      const float4 v1 = __ldcs(xin + u + gstride);
+      const float4 v2 = __ldcs(xin + u + 2u * gstride);
+      const float4 v3 = __ldcs(xin + u + 3u * gstride);
+      const int l0 = __ldg(lab_p + row);
+      const int l1 = __ldg(lab_p + row + drow);
+      const int l2 = __ldg(lab_p + row + 2u * drow);
+      const int l3 = __ldg(lab_p + row + 3u * drow);
+      do_unit(v0, l0);
+      do_unit(v1, l1);
+      do_unit(v2, l2);
+      do_unit(v3, l3);
+      u += 4u * gstride;
+      row += 4u * drow;
+      ap[0] += (double)fp0; ap[1] += (double)fp1; ap[2] += (double)fp2; ap[3] += (double)fp3;
+      fp0 = fp1 = fp2 = fp3 = 0.f;
+    }
+    for (; u < units; u += gstride, row += drow) do_unit(__ldcs(xin + u), __ldg(lab_p + row));
+    ap[0] += (double)fp0; ap[1] += (double)fp1; ap[2] += (double)fp2; ap[3] += (double)fp3;
+  }
+
+  // ordered in-block reduction: output j = (kind, class) sums the threads that own that class
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s_part[(size_t)threadIdx.x * 8 + k] = ai[k];
+    s_part[(size_t)threadIdx.x * 8 + 4 + k] = ap[k];
+  }
+  __syncthreads();
+  double* mine = prm.partials + (size_t)blockIdx.x * 2 * C;
+  const unsigned col0 = (blockIdx.x * blockDim.x) % cv;   // column of thread 0
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    const int kind = j / C, c = j % C;
+    const unsigned want = (unsigned)c / 4u;                       // owning column
+    unsigned t = (want + cv - col0) % cv;                         // first thread with that column
+    double v = 0.0;
+    for (; t < blockDim.x; t += cv) v += s_part[(size_t)t * 8 + kind * 4 + (c & 3)];
+    mine[j] = v;
+  }
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+      double v = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(prm.partials + (size_t)b * 2 * C + j);
+      prm.stats_out[RN_STATS_HEADER + C + j] = v;  // INTER block then PSUM block
+    }
+    if (threadIdx.x == 0) *prm.ticket = 0;
+  }
+}
+
 // ---- dense-label statistics (compat API): M = rows, num_fg = #rows with max z > 0.5, n_pos ------
 __global__ void dense_label_stats_kernel(long long rows, int C, const float* __restrict__ labels, double* stats) {
   int n_fg = 0;
@@ -1098,6 +1199,15 @@ static unsigned persistent_grid(K kernel, int threads, size_t smem, long long wo
 static int launch_fast(const Segs& segs, const FastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st);
 
+static unsigned gcd_u(unsigned a, unsigned b) {
+  while (b) {
+    const unsigned t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
 static unsigned loss_grid(long long units, int threads, int per_sm) {
   long long blocks = (units + threads - 1) / threads;
   long long cap = (long long)num_sms() * per_sm;
@@ -1128,15 +1238,6 @@ static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaS
     launch_cls<MODE, DICE, true>(vec4, grid, smem, st, segs, prm);
   else
     launch_cls<MODE, DICE, false>(vec4, grid, smem, st, segs, prm);
-}
-
-static unsigned gcd_u(unsigned a, unsigned b) {
-  while (b) {
-    const unsigned t = a % b;
-    a = b;
-    b = t;
-  }
-  return a;
 }
 
 template <int MODE, bool DICE, bool BF16>
@@ -1253,6 +1354,21 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   bool rows32 = true;
   for (int i = 0; i < rows->num_segments; ++i)
     if (rows->rows[i] >= (1ll << 31) - (1ll << 26)) rows32 = false;
+  bool units32 = true;
+  for (int i = 0; i < rows->num_segments; ++i)
+    if ((unsigned long long)rows->rows[i] * (unsigned)prm.cv + (1ull << 24) >= (1ull << 32)) units32 = false;
+  if (!dense_labels && vec4 && g_fast_kernels && units32 && prm.cv <= kLossThreads) {
+    const size_t fsmem = (size_t)kLossThreads * 8 * sizeof(double);
+    unsigned g = persistent_grid(cls_sums_flat_kernel, kLossThreads, fsmem,
+                                 (total_rows * prm.cv + 3) / 4);
+    const unsigned q = (unsigned)prm.cv / gcd_u((unsigned)prm.cv, (unsigned)kLossThreads);
+    const unsigned gf = g / q * q;
+    if (gf > 0 && (g - gf) * 25u <= g) {
+      cls_sums_flat_kernel<<<gf, kLossThreads, fsmem, st>>>(segs, prm);
+      RN_CUDA_CHECK_LAUNCH("rn_cls_sums(flat)");
+      return RN_OK;
+    }
+  }
   if (!dense_labels && vec4 && g_fast_kernels && rows32 && prm.cv <= 256) {
     prm.ry = 256 / prm.cv > 0 ? 256 / prm.cv : 1;
     const int fthreads = prm.cv * prm.ry;
