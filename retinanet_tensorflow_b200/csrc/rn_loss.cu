@@ -964,38 +964,56 @@ struct HuberParams {
 __global__ void __launch_bounds__(kLossThreads)
 huber_kernel(const __grid_constant__ Segs segs, const __grid_constant__ HuberParams prm) {
   __shared__ double s_red[32];
-  const long long total = segs.start[RN_MAX_LEVELS];
   const double nfg = prm.stats[RN_STAT_NUM_FG];
   const float gscale = nfg > 0 ? (float)(1.0 / (4.0 * nfg)) : 0.0f;
+  const bool by_label = prm.label.p[0] != nullptr;
+  const bool write = prm.dpred.p[0] != nullptr;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
   double acc = 0.0;
-  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total;
-       r += (long long)gridDim.x * blockDim.x) {
-    const int s = seg_of(segs, r);
-    const long long rl = r - segs.start[s];
-    bool fg;
-    if (prm.label.p[0]) {
-      fg = __ldg(reinterpret_cast<const int32_t*>(prm.label.p[s]) + rl) >= 0;
-    } else {
-      fg = reinterpret_cast<const unsigned char*>(prm.fg_mask.p[s])[rl] != 0;
-    }
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (fg) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(prm.pred.p[s]) + rl);
-      const float4 t = __ldg(reinterpret_cast<const float4*>(prm.target.p[s]) + rl);
-      const float e[4] = {fsub(p.x, t.x), fsub(p.y, t.y), fsub(p.z, t.z), fsub(p.w, t.w)};
-      float ls = 0.f, gg[4];
+
+  for (int s = 0; s < segs.num; ++s) {
+    const long long rows = segs.rows[s];
+    const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
+    const unsigned char* __restrict__ fg_p = reinterpret_cast<const unsigned char*>(prm.fg_mask.p[s]);
+    const float4* __restrict__ pred = reinterpret_cast<const float4*>(prm.pred.p[s]);
+    const float4* __restrict__ targ = reinterpret_cast<const float4*>(prm.target.p[s]);
+    float4* __restrict__ out = reinterpret_cast<float4*>(prm.dpred.p[s]);
+
+    auto one_row = [&](long long r, bool fg) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fg) {  // ~1 % of the rows
+        const float4 p = __ldg(pred + r);
+        const float4 t = __ldg(targ + r);
+        const float e[4] = {fsub(p.x, t.x), fsub(p.y, t.y), fsub(p.z, t.z), fsub(p.w, t.w)};
+        float ls = 0.f, gg[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float ae = fabsf(e[k]);
-        const float q = fminf(ae, 1.0f);
-        ls += fadd(0.5f * fmul(q, q), fsub(ae, q));  // 0.5 q^2 + delta (|e| - q)
-        gg[k] = fminf(fmaxf(e[k], -1.0f), 1.0f) * gscale;
+        for (int k = 0; k < 4; ++k) {
+          const float ae = fabsf(e[k]);
+          const float q = fminf(ae, 1.0f);
+          ls += fadd(0.5f * fmul(q, q), fsub(ae, q));  // 0.5 q^2 + delta (|e| - q)
+          gg[k] = fminf(fmaxf(e[k], -1.0f), 1.0f) * gscale;
+        }
+        acc += (double)ls;
+        g = make_float4(gg[0], gg[1], gg[2], gg[3]);
       }
-      acc += (double)ls;
-      g = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      if (write) __stcs(out + r, g);
+    };
+    auto is_fg = [&](long long r) {
+      return by_label ? (__ldg(lab_p + r) >= 0) : (fg_p[r] != 0);
+    };
+
+    long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // four rows per iteration: the four label loads are issued before the four 16-byte stores
+    for (; r + 3 * gstride < rows; r += 4 * gstride) {
+      const bool f0 = is_fg(r), f1 = is_fg(r + gstride), f2 = is_fg(r + 2 * gstride), f3 = is_fg(r + 3 * gstride);
+      one_row(r, f0);
+      one_row(r + gstride, f1);
+      one_row(r + 2 * gstride, f2);
+      one_row(r + 3 * gstride, f3);
     }
-    if (prm.dpred.p[0]) __stcs(reinterpret_cast<float4*>(prm.dpred.p[s]) + rl, g);
+    for (; r < rows; r += gstride) one_row(r, is_fg(r));
   }
+
   acc = block_sum(acc, s_red);
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
@@ -1596,7 +1614,7 @@ extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, co
   prm.ticket = reinterpret_cast<unsigned*>(d_workspace);
   prm.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_workspace) + 256);
   cudaMemsetAsync(prm.ticket, 0, sizeof(unsigned), st);
-  const unsigned grid = loss_grid(segs.start[RN_MAX_LEVELS], kLossThreads, 8);
+  const unsigned grid = persistent_grid(huber_kernel, kLossThreads, 0, (segs.start[RN_MAX_LEVELS] + 3) / 4);
   huber_kernel<<<grid, kLossThreads, 0, st>>>(segs, prm);
   RN_CUDA_CHECK_LAUNCH("rn_huber_fwd_bwd");
   return RN_OK;
