@@ -155,6 +155,29 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
 }
 
 // Segment lookup: which segment does global row `r` fall in.
+// Reserve one slot of the per-image candidate list `count[b]` for every calling lane.  Lanes that are
+// converged here and append to the same list share one atomic (opportunistic warp aggregation), and a
+// list that is already full is not touched again -- so a dense firing pattern (most anchors above the
+// threshold) costs one L2 read per warp instead of an atomic per candidate.  Returns the slot; a slot
+// >= capacity means "dropped" (the caller raises RN_FLAG_CAND_OVERFLOW).
+__device__ __forceinline__ int reserve_slot(int32_t* count, int b, int capacity) {
+  const unsigned act = __activemask();
+  const unsigned same = __match_any_sync(act, b);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(same) - 1;
+  int base = capacity;
+  if (lane == leader) {
+    if (__ldcg(count + b) < capacity) base = atomicAdd(count + b, __popc(same));
+  }
+  base = __shfl_sync(same, base, leader);
+  return base + __popc(same & ((1u << lane) - 1u));
+}
+
+// Raise a status bit at most a few times per grid (not once per event).
+__device__ __forceinline__ void raise_flag(uint32_t* status, uint32_t flag) {
+  if (status && !(__ldcg(status) & flag)) atomicOr(status, flag);
+}
+
 __device__ __forceinline__ int seg_of(const Segs& s, long long r) {
   int k = 0;
 #pragma unroll

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Seg
       const long long per_image = segs.rows[s] / prm.images;
       const int b = (int)(rl / per_image);
       const int anchor = (int)(segs.start[s] / prm.images + (rl - (long long)b * per_image));
-      const int slot = atomicAdd(prm.count + b, 1);
+      const int slot = reserve_slot(prm.count, b, prm.capacity);
       if (slot < prm.capacity) {
         const size_t o = (size_t)b * prm.capacity + slot;
         prm.ws_anchor[o] = anchor;

@@ -360,14 +360,14 @@ __device__ __noinline__ UnitOut fast_slow_unit(FastCtx cx, const FastParams& prm
       const unsigned per_image = (unsigned)(segs.rows[s] / prm.sel_images);
       const unsigned bimg = row / per_image;
       const int anchor = (int)(segs.start[s] / prm.sel_images) + (int)(row - bimg * per_image);
-      const int slot = atomicAdd(prm.sel_count + bimg, 1);
+      const int slot = reserve_slot(prm.sel_count, (int)bimg, prm.sel_capacity);
       if (slot < prm.sel_capacity) {
         const size_t o = (size_t)bimg * prm.sel_capacity + slot;
         prm.sel_anchor[o] = anchor;
         prm.sel_score[o] = bp;
         prm.sel_class[o] = bc;
-      } else if (prm.status) {
-        atomicOr(prm.status, RN_FLAG_CAND_OVERFLOW);
+      } else {
+        raise_flag(prm.status, RN_FLAG_CAND_OVERFLOW);
       }
     }
   }
