@@ -553,11 +553,16 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastP
     float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);   // four short float accumulators
 
     // four logits of one row: classify, compute
-    auto do_quad = [&](unsigned rr, unsigned c4, const float4& v, int lab, float4& g) {
+    // `full_warp`: all 32 lanes are here (main loop), so the bulk/careful choice is made per warp: when any
+    // lane needs the careful path every lane takes it (it is valid for all units) instead of running both
+    // paths one after the other under divergence.
+    auto do_quad = [&](unsigned rr, unsigned c4, const float4& v, int lab, float4& g, bool full_warp) {
       float4 l;
       const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
       const bool plain = xmax <= -0.70f && (unsigned)(lab - (int)c4) >= 4u;   // also true for IGNORE (< 0)
-      if (plain && xmax <= trig) {
+      bool bulk = plain && xmax <= trig;
+      if (full_warp) bulk = __all_sync(0xffffffffu, bulk);
+      if (bulk) {
         if (lab != RN_LABEL_IGNORE) {
           fast_bulk_unit<MODE, DICE>(cx, c4, v, g, l);
           acc4.x += l.x; acc4.y += l.y; acc4.z += l.z; acc4.w += l.w;
@@ -572,17 +577,17 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastP
       }
     };
     // one 16-byte unit
-    auto do_unit = [&](unsigned uu, unsigned rr, unsigned cc, const Unit& raw, int lab) {
+    auto do_unit = [&](unsigned uu, unsigned rr, unsigned cc, const Unit& raw, int lab, bool full_warp) {
       Unit out;
       if constexpr (BF16) {
         float4 lo, hi, glo, ghi;
         unpack_bf16x8(raw, lo, hi);
-        do_quad(rr, cc * 8u, lo, lab, glo);
-        do_quad(rr, cc * 8u + 4u, hi, lab, ghi);
+        do_quad(rr, cc * 8u, lo, lab, glo, full_warp);
+        do_quad(rr, cc * 8u + 4u, hi, lab, ghi, full_warp);
         out = pack_bf16x8(glo, ghi);
       } else {
         float4 g;
-        do_quad(rr, cc * 4u, *reinterpret_cast<const float4*>(&raw), lab, g);
+        do_quad(rr, cc * 4u, *reinterpret_cast<const float4*>(&raw), lab, g, full_warp);
         out = *reinterpret_cast<const Unit*>(&g);
       }
       if (write_grad) __stcs(gout + uu, out);
@@ -590,7 +595,9 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastP
 
     // main loop: four units per iteration, all loads first, no bounds tests
     // (u + 4*gstride cannot wrap: units + 2^24 < 2^32 is part of the host-side check)
-    while (u + 3u * gstride < units) {
+    // (u | 31) is the warp's last lane (u - lane and gstride are multiples of 32): the condition is the same
+    // for all 32 lanes, which the __all_sync in do_quad relies on
+    while ((u | 31u) + 3u * gstride < units) {
       unsigned r1, r2, r3, c1, c2, c3;
       if (FIXED_COL) {
         r1 = row + drow; r2 = r1 + drow; r3 = r2 + drow;
@@ -608,10 +615,10 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastP
       const int l1 = __ldg(lab_p + r1);
       const int l2 = __ldg(lab_p + r2);
       const int l3 = __ldg(lab_p + r3);
-      do_unit(u, row, col, v0, l0);
-      do_unit(u + gstride, r1, c1, v1, l1);
-      do_unit(u + 2u * gstride, r2, c2, v2, l2);
-      do_unit(u + 3u * gstride, r3, c3, v3, l3);
+      do_unit(u, row, col, v0, l0, true);
+      do_unit(u + gstride, r1, c1, v1, l1, true);
+      do_unit(u + 2u * gstride, r2, c2, v2, l2, true);
+      do_unit(u + 3u * gstride, r3, c3, v3, l3, true);
       u += 4u * gstride;
       if (FIXED_COL) {
         row = r3 + drow;
@@ -619,11 +626,11 @@ cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastP
         col = c3 + dcol; row = r3 + drow; if (col >= cv) { col -= cv; row += 1; }
       }
     }
-    // tail: at most three units
+    // tail: the last few units of each lane
     for (; u < units; u += gstride) {
       const Unit v = __ldcs(xin + u);
       const int lab = __ldg(lab_p + row);
-      do_unit(u, row, col, v, lab);
+      do_unit(u, row, col, v, lab, false);
       col += dcol;
       row += drow;
       if (col >= cv) {
