@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument('--topk', type=int, default=1000)
     ap.add_argument('--no-overlap', action='store_true', help='keep the detection tail on the main stream')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
+    ap.add_argument('--graph', action='store_true',
+                    help='replay the step as one CUDA graph (DenseHeadPath.capture); single GPU, for launch-bound '
+                         'small workloads')
     ap.add_argument('--logit-sigma', type=float, default=1.0,
                     help='std of the synthetic background logits around the prior (SURVEY 8d text says 1.5, which makes '
                          '8.5%% of anchors fire instead of the ~1%% it asks for; default 1.0 gives ~1%%)')
@@ -363,8 +366,21 @@ def run_b200(args):
 
     path.stage_hook = timed
     overlap = not args.no_overlap
+    graph = None
+    if args.graph:
+        if world > 1:
+            raise SystemExit('--graph is single-GPU')
+        graph = path.capture(gt_boxes, gt_classes, gt_counts, logits, regs)
+        overlap = False
+
+    def one_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
+
     for _ in range(args.warmup):
-        path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
+        one_step()
     barrier()
     sampler = ClockSampler('GPU-' + str(torch.cuda.get_device_properties(dev).uuid))
     if rank == 0:
@@ -374,12 +390,20 @@ def run_b200(args):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for _ in range(args.steps):
-        path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
+        one_step()
     path.join()          # the timed region ends when the last step's detections are done too
     end.record()
     barrier()
-    record['on'] = False
     launches = _lib.lib.rn_launch_count() - launches0
+    if graph is not None:
+        # kernels inside a replayed graph are not visible to the host-side counter or the stage events: count
+        # and time them on a few eager steps after the timed region
+        l0 = _lib.lib.rn_launch_count()
+        for _ in range(10):
+            path.step(gt_boxes, gt_classes, gt_counts, logits, regs)
+        torch.cuda.synchronize()
+        launches = (_lib.lib.rn_launch_count() - l0) // 10 * args.steps
+    record['on'] = False
     clocks = sampler.stop() if rank == 0 else None
     ms = start.elapsed_time(end)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -480,6 +504,7 @@ def run_b200(args):
             'fused_loss_select': bool(path.fused_select_supported()),
             'stats_exchange': ('peer-memory kernel' if path._peer is not None else 'nccl') if world > 1 else None,
             'detect_tail_on_side_stream': bool(overlap and path.fused_select_supported()),
+            'cuda_graph': graph is not None,
             'cpu_baseline': cpu_baseline,
             'check': {'class_loss': loss_vals[0], 'regr_loss': loss_vals[1], 'num_fg': loss_vals[2],
                       'candidates': cand_total, 'detections': det_total},

@@ -367,6 +367,31 @@ class DenseHeadPath(object):
             self._side_done.record(self._side)
         return self.loss_out, self.det_count
 
+    def capture(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True, warmup=2):
+        """Record one whole `step()` on these (static) buffers into a CUDA graph and return it;
+        `graph.replay()` then re-runs the step with one launch -- for small workloads (Shapes, VOC, small
+        batches) the ~10 kernel launches of a step cost more than the kernels.  Refill the same input
+        tensors in place between replays; outputs land in the usual members (loss_out, dlogits, det_*).
+        Single rank only: the peer-memory exchange takes a per-call epoch argument."""
+        if self._multi_rank():
+            raise RuntimeError('DenseHeadPath.capture: graph capture is single-rank (the statistics exchange '
+                               'carries a per-call epoch); call step() instead')
+        self.join()
+        hook, self.stage_hook = self.stage_hook, None
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):     # warm-up outside the capture: allocates dlogits / dreg
+                for _ in range(max(1, warmup)):
+                    self.step(gt_boxes, gt_classes, gt_counts, logits, regression, fused=fused)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.step(gt_boxes, gt_classes, gt_counts, logits, regression, fused=fused)
+        finally:
+            self.stage_hook = hook
+        return graph
+
     def join(self):
         """Make the current stream wait for an overlapped detection tail."""
         if self._side_done is not None:

@@ -303,3 +303,33 @@ def test_nms_degenerate_and_flipped_boxes():
     want = oracle.nms_classwise(oracle.BoxesDecoded(boxes, scores, classes), 1, return_indices=True)[1]
     np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(got, [0, 2, 3])
+
+
+def test_cuda_graph_replay_matches_eager_steps():
+    """DenseHeadPath.capture: the replayed graph follows in-place input updates and reproduces step()."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    wl, path, logits, regs = _case('voc', 2, capacity=8192)
+    boxes, classes, counts = synthetic.gt_batch(wl, 2)
+    gt = [torch.from_numpy(x).cuda() for x in (boxes, classes, counts)]
+    lg, rg = logits.clone(), regs.clone()
+    graph = path.capture(*gt, lg, rg)
+    for i in range(3):
+        cur_l, cur_r = logits + 0.05 * i, regs * (1.0 + 0.01 * i)
+        path.step(*gt, cur_l, cur_r)
+        torch.cuda.synchronize()
+        want = [x.clone() for x in (path.loss_out, path.dlogits, path.dreg, path.det_count, path.det_index,
+                                    path.det_boxes)]
+        for x in (path.dlogits, path.dreg, path.det_index, path.det_boxes, path.loss_out):
+            x.zero_()
+        lg.copy_(cur_l)
+        rg.copy_(cur_r)
+        graph.replay()
+        torch.cuda.synchronize()
+        path.check_status()
+        assert torch.equal(path.loss_out, want[0]) and torch.equal(path.dlogits, want[1])
+        assert torch.equal(path.dreg, want[2]) and torch.equal(path.det_count, want[3])
+        for b in range(2):
+            m = int(want[3][b])
+            assert m > 0
+            assert torch.equal(path.det_index[b, :m], want[4][b, :m]) and torch.equal(path.det_boxes[b, :m], want[5][b, :m])
