@@ -212,9 +212,10 @@ RN_API size_t rn_loss_workspace_bytes(int num_classes);
 
 /* Per-class sums needed before a dice gradient (losses.py:53-56): WRITES I_c and sum p into
  * d_stats.  dense_labels == 0: label maps are int32 compact; 1: float [rows, C] (every row
- * trainable). */
+ * trainable).  logits_dtype: RN_DTYPE_F32, or RN_DTYPE_BF16 (compact labels, C % 8 == 0;
+ * float32 math on bfloat16 logits). */
 RN_API int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits,
-                       const rn_maps_t* label, int dense_labels, double* d_stats,
+                       const rn_maps_t* label, int dense_labels, int logits_dtype, double* d_stats,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Fused classification loss forward + backward in one pass over the logits
@@ -304,19 +305,23 @@ RN_API int rn_boxmap_op(const rn_pyramid_t* pyr, int batch, int op, const rn_map
 RN_API int rn_classmap_fg(int64_t rows, int num_classes, const float* d_classmap, float thr,
                           uint8_t* d_fg_mask, void* stream);
 
+#define RN_SCORES_LOGITS 1
+#define RN_SCORES_BF16 2
+
 RN_API size_t rn_select_workspace_bytes(int batch, int capacity);
 
 /* utils.boxes_decode + merge_boxes_decoded (utils.py:183-195,223-227) for a batch:
  * per anchor score = max_c prob, class = argmax_c prob (first maximum), keep score >
  * score_thr (strict), candidates of image b in ascending level-major anchor order.
- *   scores maps: f32 [.., C]; scores_are_logits != 0 applies sigmoid in-kernel.
+ *   scores maps: [.., C]; score_format = RN_SCORES_LOGITS (apply sigmoid in-kernel) |
+ *                RN_SCORES_BF16 (bfloat16 instead of float32; C % 8 == 0); 0 = f32 probabilities.
  *   regs maps:   f32 [.., 4]; regs_are_deltas != 0 decodes them on the fly (needs pyr),
  *                otherwise they are already corner boxes (pyr may describe geometry only).
  *   topk_per_level > 0: NOT in the reference -- keep the k best of each (image, level)
  *                (ties -> lower anchor), identity when k >= #candidates.
  * Outputs [B, capacity, .]; d_cand_anchor = anchor index within the image; d_cand_count [B]. */
 RN_API int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_classes,
-                            const rn_maps_t* scores, int scores_are_logits, const rn_maps_t* regs,
+                            const rn_maps_t* scores, int score_format, const rn_maps_t* regs,
                             int regs_are_deltas, float score_thr, int topk_per_level, int capacity,
                             float* d_cand_boxes, float* d_cand_scores, int32_t* d_cand_classes,
                             int32_t* d_cand_anchor, int32_t* d_cand_count, uint32_t* d_status,

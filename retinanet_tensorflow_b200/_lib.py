@@ -21,6 +21,7 @@ RN_LABEL_IGNORE = -2
 RN_CLS_NONE, RN_CLS_FOCAL, RN_CLS_BCE, RN_CLS_BALANCED_BCE = 0, 1, 2, 3
 RN_CLS_DICE_FLAG = 16
 RN_DTYPE_F32, RN_DTYPE_BF16 = 0, 1
+RN_SCORES_LOGITS, RN_SCORES_BF16 = 1, 2
 
 RN_STAT_TRAINABLE, RN_STAT_NUM_FG, RN_STAT_CLS_SUM, RN_STAT_HUBER_SUM = 0, 1, 2, 3
 
@@ -91,7 +92,7 @@ PROTOTYPES = {
     'rn_label_stats': (_i, [_RP, _i, _MP, _vp, _vp]),
     'rn_label_stats_dense': (_i, [_i64, _i, _vp, _vp, _vp]),
     'rn_loss_workspace_bytes': (_sz, [_i]),
-    'rn_cls_sums': (_i, [_RP, _i, _MP, _MP, _i, _vp, _vp, _sz, _vp]),
+    'rn_cls_sums': (_i, [_RP, _i, _MP, _MP, _i, _i, _vp, _vp, _sz, _vp]),
     'rn_cls_loss_fwd_bwd': (_i, [_RP, _i, _MP, _MP, _i, _i, _f, _f, _f, _MP, _i, _vp, _vp, _sz, _vp]),
     'rn_huber_fwd_bwd': (_i, [_RP, _MP, _MP, _MP, _MP, _MP, _vp, _vp, _sz, _vp]),
     'rn_huber_rows': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -12,6 +12,7 @@
 //              (image, class) runs the greedy pass -- 32 candidates at a time against the kept
 //              boxes staged in shared memory, then resolves the 32 among themselves with
 //              __ballot_sync masks; one CTA per image compacts class-major.
+#include <cuda_bf16.h>
 #include "rn_common.cuh"
 #include "rn_tiles.cuh"
 
@@ -149,22 +150,58 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Seg
   const long long iters = (total_rows + num_groups - 1) / num_groups;
   unsigned flags = 0;
 
+  // bf16x8 rows are half the bytes of float32 rows, so one row group per iteration does not keep enough
+  // bytes in flight: the next iteration's units are requested before this one's are used.
+  constexpr int kRaw = VEC == 8 ? UPL : 1;
+  uint4 cur[kRaw];
+  auto fetch = [&](long long it, uint4 (&raw)[kRaw]) {
+    const long long r = group + it * num_groups;
+    const bool ok = r < total_rows;
+    const uint4* base = nullptr;
+    if (ok) {
+      const int s = seg_of(segs, r);
+      base = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(prm.scores.p[s]) +
+                                            (r - segs.start[s]) * C);
+    }
+#pragma unroll
+    for (int j = 0; j < kRaw; ++j) {
+      const int u = sub + j * LPR;
+      raw[j] = (ok && u < upr) ? __ldcs(base + u) : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // -inf
+    }
+  };
+  if constexpr (VEC == 8) {
+    if (iters > 0) fetch(0, cur);
+  }
+
   for (long long it = 0; it < iters; ++it) {
     const long long r = group + it * num_groups;
     const bool row_ok = r < total_rows;
+    uint4 nxt[kRaw];
+    if constexpr (VEC == 8) {
+      if (it + 1 < iters) fetch(it + 1, nxt);
+    }
     int s = 0;
     long long rl = 0;
-    const float* base = nullptr;
+    const float* base = nullptr;   // (a bfloat16 row when VEC == 8: C * 2 bytes)
     if (row_ok) {
       s = seg_of(segs, r);
       rl = r - segs.start[s];
-      base = reinterpret_cast<const float*>(prm.scores.p[s]) + rl * C;
+      base = VEC == 8 ? reinterpret_cast<const float*>(reinterpret_cast<const __nv_bfloat16*>(prm.scores.p[s]) + rl * C)
+                      : reinterpret_cast<const float*>(prm.scores.p[s]) + rl * C;
     }
     float v[UPL][VEC];
 #pragma unroll
     for (int j = 0; j < UPL; ++j) {
       const int u = sub + j * LPR;
-      if (row_ok && u < upr) {
+      if constexpr (VEC == 8) {   // bf16x8: one 128-bit access (already in flight), widened to float32
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&cur[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(h[k]);
+          v[j][2 * k] = f.x;
+          v[j][2 * k + 1] = f.y;
+        }
+      } else if (row_ok && u < upr) {
         if constexpr (VEC == 4) {
           const float4 t = ld_stream4(base + u * 4);
           v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
@@ -256,6 +293,10 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Seg
       } else {
         flags |= RN_FLAG_CAND_OVERFLOW;
       }
+    }
+    if constexpr (VEC == 8) {
+#pragma unroll
+      for (int j = 0; j < kRaw; ++j) cur[j] = nxt[j];
     }
   }
   if (prm.status) {
@@ -694,7 +735,7 @@ extern "C" size_t rn_select_workspace_bytes(int batch, int capacity) {
 }
 
 extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* scores,
-                                int scores_are_logits, const rn_maps_t* regs, int regs_are_deltas, float score_thr,
+                                int score_format, const rn_maps_t* regs, int regs_are_deltas, float score_thr,
                                 int topk_per_level, int capacity, float* d_cand_boxes, float* d_cand_scores,
                                 int32_t* d_cand_classes, int32_t* d_cand_anchor, int32_t* d_cand_count,
                                 uint32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream) {
@@ -710,18 +751,23 @@ extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_clas
   rn_rows_t rows;
   rn_rows_from_pyramid(pyr, batch, &rows);
   const Segs segs = make_segs(&rows);
+  RN_REQUIRE(score_format >= 0 && score_format <= 3, RN_ERR_BAD_ARG, "rn_decode_select: unknown score_format");
+  const bool bf16 = (score_format & RN_SCORES_BF16) != 0;
+  const int scores_are_logits = score_format & RN_SCORES_LOGITS;
   bool vec4 = num_classes % 4 == 0;
   for (int l = 0; l < pyr->num_levels; ++l) {
     RN_REQUIRE(scores->p[l] && regs->p[l], RN_ERR_BAD_ARG, "rn_decode_select: missing map for level %d", l);
     RN_REQUIRE(((uintptr_t)regs->p[l] & 15) == 0, RN_ERR_BAD_ARG, "regs maps must be 16-byte aligned");
     if ((uintptr_t)scores->p[l] & 15) vec4 = false;
   }
+  RN_REQUIRE(!bf16 || (num_classes % 8 == 0 && vec4), RN_ERR_UNSUPPORTED,
+             "rn_decode_select: bfloat16 scores need num_classes %% 8 == 0 and 16-byte aligned maps");
   const size_t n = (size_t)batch * capacity;
   char* ws = (char*)d_workspace;
   SelectParams sp;
   sp.scores = make_ptrs(scores);
   sp.num_classes = num_classes;
-  sp.units_per_row = vec4 ? num_classes / 4 : num_classes;
+  sp.units_per_row = bf16 ? num_classes / 8 : (vec4 ? num_classes / 4 : num_classes);
   sp.images = batch;
   sp.capacity = capacity;
   sp.thr = score_thr;
@@ -731,17 +777,19 @@ extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_clas
   sp.ws_class = (int32_t*)ws; ws += align256(n * 4);
   sp.count = d_cand_count;
   sp.status = d_status;
+  const int max_upl = 8;   // 16-byte loads per lane and row (bf16x8 units: up to 64 classes per lane)
   int lpr = 1;
-  while (lpr < 32 && (sp.units_per_row + lpr - 1) / lpr > 8) lpr <<= 1;
+  while (lpr < 32 && (sp.units_per_row + lpr - 1) / lpr > max_upl) lpr <<= 1;
   const int upl = (sp.units_per_row + lpr - 1) / lpr;
-  RN_REQUIRE(upl <= 8, RN_ERR_UNSUPPORTED, "rn_decode_select: more than %d classes", vec4 ? 1024 : 256);
+  RN_REQUIRE(upl <= max_upl, RN_ERR_UNSUPPORTED, "rn_decode_select: more than %d classes", vec4 ? 1024 : 256);
   cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * batch, st);
   const long long total_rows = segs.start[RN_MAX_LEVELS];
   long long blocks = (total_rows * lpr + 255) / 256;
   const long long capb = (long long)num_sms() * 8;
   if (blocks > capb) blocks = capb;
   if (blocks < 1) blocks = 1;
-  if (vec4) launch_select_lpr<4>(lpr, upl, (unsigned)blocks, st, segs, sp);
+  if (bf16) launch_select_lpr<8>(lpr, upl, (unsigned)blocks, st, segs, sp);
+  else if (vec4) launch_select_lpr<4>(lpr, upl, (unsigned)blocks, st, segs, sp);
   else launch_select_lpr<1>(lpr, upl, (unsigned)blocks, st, segs, sp);
   RN_CUDA_CHECK_LAUNCH("rn_decode_select(select)");
 

@@ -333,6 +333,23 @@ __device__ __forceinline__ float bce_neg_bulk(float x, float& p) {
   return fmaf(e * e, t, e);
 }
 
+__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float4& lo, float4& hi) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  const float2 c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+  lo = make_float4(a.x, a.y, b.x, b.y);
+  hi = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float4& lo, const float4& hi) {
+  uint4 r;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+  h[0] = __floats2bfloat162_rn(lo.x, lo.y);
+  h[1] = __floats2bfloat162_rn(lo.z, lo.w);
+  h[2] = __floats2bfloat162_rn(hi.x, hi.y);
+  h[3] = __floats2bfloat162_rn(hi.z, hi.w);
+  return r;
+}
+
 // Per-thread state of the fast kernel that both the hot loop and the rare path need.
 struct FastCtx {
   const float* s_tab;   // [4][C] w_neg, w_pos, dice A, dice B (shared memory)
@@ -491,24 +508,7 @@ __device__ __forceinline__ void fast_bulk_unit(const FastCtx cx, unsigned c4, fl
 // FIXED_COL: the grid stride is a multiple of the row length, so a thread's float4 column never
 // changes and its row advances by a constant (no wrap test in the loop).
 // BF16: logits and gradients are bfloat16 (a unit is 8 logits = one 128-bit access, "bf16x8"); the math
-// stays float32.  C % 8 == 0; not combined with DICE.
-__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float4& lo, float4& hi) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-  const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
-  const float2 c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
-  lo = make_float4(a.x, a.y, b.x, b.y);
-  hi = make_float4(c.x, c.y, d.x, d.y);
-}
-__device__ __forceinline__ uint4 pack_bf16x8(const float4& lo, const float4& hi) {
-  uint4 r;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
-  h[0] = __floats2bfloat162_rn(lo.x, lo.y);
-  h[1] = __floats2bfloat162_rn(lo.z, lo.w);
-  h[2] = __floats2bfloat162_rn(hi.x, hi.y);
-  h[3] = __floats2bfloat162_rn(hi.z, hi.w);
-  return r;
-}
-
+// stays float32.  C % 8 == 0.
 template <int MODE, bool DICE, int MINB, bool SELECT, bool FIXED_COL, bool BF16>
 __global__ void __launch_bounds__(kLossThreads, MINB)
 cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastParams prm) {
@@ -860,18 +860,27 @@ __global__ void __launch_bounds__(512) cls_sums_fast_kernel(const __grid_constan
 // constant and the per-class sums live in registers for the whole kernel; four units per
 // iteration with all loads first.  The in-block reduction is ordered (thread order), so the result
 // is run-to-run deterministic.
-template <int U, int MINB>   // U units (float4 loads) in flight per thread, MINB resident CTAs per SM
+template <int U, int MINB, bool BF16>   // U 16-byte loads in flight per thread, MINB resident CTAs per SM
 __global__ void __launch_bounds__(kLossThreads, MINB)
 cls_sums_flat_kernel(const __grid_constant__ Segs segs, const __grid_constant__ SumsParams prm) {
-  extern __shared__ double s_part[];   // [blockDim][8]: I[4], P[4] of every thread
+  constexpr int K = BF16 ? 8 : 4;      // classes per 16-byte unit (bf16x8 or float4)
+  extern __shared__ double s_part[];   // [blockDim][2K]: I[K], P[K] of every thread
   const int C = prm.num_classes;
   const unsigned cv = (unsigned)prm.cv;
   const unsigned gstride = gridDim.x * blockDim.x;   // multiple of cv (host)
   const unsigned drow = gstride / cv;
   const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned col = gtid % cv;
-  const int c4 = (int)col * 4;
-  double ai[4] = {0, 0, 0, 0}, ap[4] = {0, 0, 0, 0};
+  const int c0 = (int)col * K;
+  // sum of p per class in double; sum of z*p gets a handful of terms per thread (a positive row reaches exactly
+  // one of the cv threads that share it), so a float is exact enough and keeps the registers for the loads
+  double ap[K];
+  float ai[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    ap[k] = 0.0;
+    ai[k] = 0.f;
+  }
 
   auto prob = [](float x) {
     if (x <= -0.70f) {  // same bulk formula as cls_fast_kernel: p = e / (1 + e), e = exp(x)
@@ -880,45 +889,67 @@ cls_sums_flat_kernel(const __grid_constant__ Segs segs, const __grid_constant__ 
     }
     return sigmoid_f32(x);
   };
+  // four sigmoids; confident negatives share ONE reciprocal (1/(abcd) times the other factors; 1 + e is in
+  // [1, 1.5], so nothing over- or underflows).  The kernel was limited by the MUFU pipe (exp2 + rcp per logit):
+  // this takes it from 8 to 5 MUFU per four logits.
+  auto prob4 = [&](const float4& v, float* p) {
+    if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) <= -0.70f) {
+      const float e0 = ex2_approx(v.x * 1.44269502163e+00f), e1 = ex2_approx(v.y * 1.44269502163e+00f);
+      const float e2 = ex2_approx(v.z * 1.44269502163e+00f), e3 = ex2_approx(v.w * 1.44269502163e+00f);
+      float i0, i1, i2, i3;
+      rcp4(1.0f + e0, 1.0f + e1, 1.0f + e2, 1.0f + e3, i0, i1, i2, i3);
+      p[0] = e0 * i0;
+      p[1] = e1 * i1;
+      p[2] = e2 * i2;
+      p[3] = e3 * i3;
+    } else {
+      p[0] = prob(v.x);
+      p[1] = prob(v.y);
+      p[2] = prob(v.z);
+      p[3] = prob(v.w);
+    }
+  };
 
   for (int s = 0; s < segs.num; ++s) {
     const unsigned units = (unsigned)segs.rows[s] * cv;
-    const float4* __restrict__ xin = reinterpret_cast<const float4*>(prm.logits.p[s]);
+    const uint4* __restrict__ xin = reinterpret_cast<const uint4*>(prm.logits.p[s]);
     const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
     unsigned u = gtid;
     unsigned row = u / cv;
-    float fp0 = 0.f, fp1 = 0.f, fp2 = 0.f, fp3 = 0.f;   // float partials of sum p, flushed per iteration
+    float fp[K];   // float partials of sum p, flushed to the doubles once per iteration
+#pragma unroll
+    for (int k = 0; k < K; ++k) fp[k] = 0.f;
 
-    auto do_unit = [&](const float4& v, int lab) {
+    auto do_unit = [&](const uint4& raw, int lab) {
       if (lab == RN_LABEL_IGNORE) return;
-      float p0, p1, p2, p3;
-      if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) <= -0.70f) {
-        // four confident negatives: p = e / (1 + e) with ONE reciprocal for the four denominators
-        // (1/(abcd) times the other factors; 1 + e is in [1, 1.5], so nothing over- or underflows).  The
-        // kernel is limited by the MUFU pipe (exp2 + rcp per logit), this takes it from 8 to 5 per unit.
-        const float e0 = ex2_approx(v.x * 1.44269502163e+00f), e1 = ex2_approx(v.y * 1.44269502163e+00f);
-        const float e2 = ex2_approx(v.z * 1.44269502163e+00f), e3 = ex2_approx(v.w * 1.44269502163e+00f);
-        float i0, i1, i2, i3;
-        rcp4(1.0f + e0, 1.0f + e1, 1.0f + e2, 1.0f + e3, i0, i1, i2, i3);
-        p0 = e0 * i0;
-        p1 = e1 * i1;
-        p2 = e2 * i2;
-        p3 = e3 * i3;
+      float p[K];
+      if constexpr (BF16) {
+        float4 lo, hi;
+        unpack_bf16x8(raw, lo, hi);
+        prob4(lo, p);
+        prob4(hi, p + 4);
       } else {
-        p0 = prob(v.x); p1 = prob(v.y); p2 = prob(v.z); p3 = prob(v.w);
+        prob4(*reinterpret_cast<const float4*>(&raw), p);
       }
-      fp0 += p0; fp1 += p1; fp2 += p2; fp3 += p3;
-      const unsigned d = (unsigned)(lab - c4);
-      if (d < 4u) {  // the row's positive class is one of mine (rare)
-        if (d == 0) ai[0] += (double)p0;
-        else if (d == 1) ai[1] += (double)p1;
-        else if (d == 2) ai[2] += (double)p2;
-        else ai[3] += (double)p3;
+#pragma unroll
+      for (int k = 0; k < K; ++k) fp[k] += p[k];
+      const unsigned d = (unsigned)(lab - c0);
+      if (d < (unsigned)K) {  // the row's positive class is one of mine (rare)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (d == (unsigned)k) ai[k] += p[k];
+      }
+    };
+    auto flush = [&]() {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        ap[k] += (double)fp[k];
+        fp[k] = 0.f;
       }
     };
 
     while (u + (unsigned)(U - 1) * gstride < units) {
-      float4 v[U];
+      uint4 v[U];
       int l[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) v[k] = __ldcs(xin + u + (unsigned)k * gstride);
@@ -928,28 +959,27 @@ cls_sums_flat_kernel(const __grid_constant__ Segs segs, const __grid_constant__ 
       for (int k = 0; k < U; ++k) do_unit(v[k], l[k]);
       u += (unsigned)U * gstride;
       row += (unsigned)U * drow;
-      ap[0] += (double)fp0; ap[1] += (double)fp1; ap[2] += (double)fp2; ap[3] += (double)fp3;
-      fp0 = fp1 = fp2 = fp3 = 0.f;
+      flush();
     }
     for (; u < units; u += gstride, row += drow) do_unit(__ldcs(xin + u), __ldg(lab_p + row));
-    ap[0] += (double)fp0; ap[1] += (double)fp1; ap[2] += (double)fp2; ap[3] += (double)fp3;
+    flush();
   }
 
   // ordered in-block reduction: output j = (kind, class) sums the threads that own that class
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    s_part[(size_t)threadIdx.x * 8 + k] = ai[k];
-    s_part[(size_t)threadIdx.x * 8 + 4 + k] = ap[k];
+  for (int k = 0; k < K; ++k) {
+    s_part[(size_t)threadIdx.x * 2 * K + k] = (double)ai[k];
+    s_part[(size_t)threadIdx.x * 2 * K + K + k] = ap[k];
   }
   __syncthreads();
   double* mine = prm.partials + (size_t)blockIdx.x * 2 * C;
   const unsigned col0 = (blockIdx.x * blockDim.x) % cv;   // column of thread 0
   for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
     const int kind = j / C, c = j % C;
-    const unsigned want = (unsigned)c / 4u;                       // owning column
+    const unsigned want = (unsigned)c / (unsigned)K;              // owning column
     unsigned t = (want + cv - col0) % cv;                         // first thread with that column
     double v = 0.0;
-    for (; t < blockDim.x; t += cv) v += s_part[(size_t)t * 8 + kind * 4 + (c & 3)];
+    for (; t < blockDim.x; t += cv) v += s_part[(size_t)t * 2 * K + kind * K + (c % K)];
     mine[j] = v;
   }
   __shared__ bool s_last;
@@ -1318,31 +1348,30 @@ static int launch_fast(const Segs& segs, const FastParams& fp, int mode, bool se
   const int base = mode & 15;
   const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
   const size_t smem = (dice || base == RN_CLS_BALANCED_BCE) ? 4 * (size_t)fp.num_classes * sizeof(float) : 0;
-  if (fp.bf16) {   // bf16x8 units; not combined with dice (checked by the callers)
-    switch (base) {
-      case RN_CLS_FOCAL: launch_fast_variant<RN_CLS_FOCAL, false, true>(segs, fp, select, work, smem, st); break;
-      case RN_CLS_BCE: launch_fast_variant<RN_CLS_BCE, false, true>(segs, fp, select, work, smem, st); break;
-      default: launch_fast_variant<RN_CLS_BALANCED_BCE, false, true>(segs, fp, select, work, smem, st); break;
-    }
-  } else {
-    switch (base) {
-      case RN_CLS_FOCAL:
-        if (dice) launch_fast_variant<RN_CLS_FOCAL, true, false>(segs, fp, select, work, smem, st);
-        else launch_fast_variant<RN_CLS_FOCAL, false, false>(segs, fp, select, work, smem, st);
-        break;
-      case RN_CLS_BCE:
-        if (dice) launch_fast_variant<RN_CLS_BCE, true, false>(segs, fp, select, work, smem, st);
-        else launch_fast_variant<RN_CLS_BCE, false, false>(segs, fp, select, work, smem, st);
-        break;
-      case RN_CLS_BALANCED_BCE:
-        if (dice) launch_fast_variant<RN_CLS_BALANCED_BCE, true, false>(segs, fp, select, work, smem, st);
-        else launch_fast_variant<RN_CLS_BALANCED_BCE, false, false>(segs, fp, select, work, smem, st);
-        break;
-      default:
-        launch_fast_variant<RN_CLS_NONE, true, false>(segs, fp, select, work, smem, st);
-        break;
-    }
+#define RN_FAST_MODES(BF)                                                                            \
+  switch (base) {                                                                                      \
+    case RN_CLS_FOCAL:                                                                                 \
+      if (dice) launch_fast_variant<RN_CLS_FOCAL, true, BF>(segs, fp, select, work, smem, st);         \
+      else launch_fast_variant<RN_CLS_FOCAL, false, BF>(segs, fp, select, work, smem, st);             \
+      break;                                                                                           \
+    case RN_CLS_BCE:                                                                                   \
+      if (dice) launch_fast_variant<RN_CLS_BCE, true, BF>(segs, fp, select, work, smem, st);           \
+      else launch_fast_variant<RN_CLS_BCE, false, BF>(segs, fp, select, work, smem, st);               \
+      break;                                                                                           \
+    case RN_CLS_BALANCED_BCE:                                                                          \
+      if (dice) launch_fast_variant<RN_CLS_BALANCED_BCE, true, BF>(segs, fp, select, work, smem, st);  \
+      else launch_fast_variant<RN_CLS_BALANCED_BCE, false, BF>(segs, fp, select, work, smem, st);      \
+      break;                                                                                           \
+    default:                                                                                           \
+      launch_fast_variant<RN_CLS_NONE, true, BF>(segs, fp, select, work, smem, st);                    \
+      break;                                                                                           \
   }
+  if (fp.bf16) {   // bf16x8 units (two float4 halves per 128-bit access)
+    RN_FAST_MODES(true)
+  } else {
+    RN_FAST_MODES(false)
+  }
+#undef RN_FAST_MODES
   RN_CUDA_CHECK_LAUNCH("fast classification-loss kernel");
   return RN_OK;
 }
@@ -1375,7 +1404,8 @@ static int check_rows(const rn_rows_t* rows, const char* who) {
 }
 
 extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits, const rn_maps_t* label,
-                           int dense_labels, double* d_stats, void* d_workspace, size_t workspace_bytes, void* stream) {
+                           int dense_labels, int logits_dtype, double* d_stats, void* d_workspace,
+                           size_t workspace_bytes, void* stream) {
   int rc = check_rows(rows, "rn_cls_sums");
   if (rc) return rc;
   RN_REQUIRE(maps_present(logits) && maps_present(label) && d_stats && d_workspace, RN_ERR_BAD_ARG,
@@ -1384,9 +1414,15 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   RN_REQUIRE(workspace_bytes >= rn_loss_workspace_bytes(num_classes), RN_ERR_CAPACITY, "rn_cls_sums: workspace too small");
   const Segs segs = make_segs(rows);
   cudaStream_t st = (cudaStream_t)stream;
+  RN_REQUIRE(logits_dtype == RN_DTYPE_F32 || logits_dtype == RN_DTYPE_BF16, RN_ERR_BAD_ARG,
+             "rn_cls_sums: unknown logits_dtype");
+  const bool bf16 = logits_dtype == RN_DTYPE_BF16;
   const bool vec4 = (num_classes % 4 == 0) && aligned16(logits, rows->num_segments) &&
                     (!dense_labels || aligned16(label, rows->num_segments));
-  const int vec = vec4 ? 4 : 1;
+  const int vec = bf16 ? 8 : (vec4 ? 4 : 1);
+  RN_REQUIRE(!bf16 || (!dense_labels && num_classes % 8 == 0 && aligned16(logits, rows->num_segments) && g_fast_kernels),
+             RN_ERR_UNSUPPORTED,
+             "rn_cls_sums: bf16 logits need compact labels, num_classes %% 8 == 0 and 16-byte aligned maps");
   SumsParams prm;
   prm.logits = make_ptrs(logits);
   prm.label = make_ptrs(label);
@@ -1408,20 +1444,27 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   bool units32 = true;
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (unsigned)prm.cv + (1ull << 24) >= (1ull << 32)) units32 = false;
-  if (!dense_labels && vec4 && g_fast_kernels && units32 && prm.cv <= kLossThreads) {
-    const size_t fsmem = (size_t)kLossThreads * 8 * sizeof(double);
+  if (!dense_labels && (vec4 || bf16) && g_fast_kernels && units32 && prm.cv <= kLossThreads) {
     // six float4 loads in flight per thread at 4 resident CTAs per SM measured best (4: 0.90 ms, 6: 0.85 ms,
     // 8 with 3 CTAs: 0.95 ms, 8 with 2 CTAs: 1.24 ms at COCO batch 64): the kernel is bound by resident warps, not
-    // by bytes in flight
-    unsigned g = persistent_grid(cls_sums_flat_kernel<6, 4>, kLossThreads, fsmem, (total_rows * prm.cv + 3) / 4);
-    const unsigned q = (unsigned)prm.cv / gcd_u((unsigned)prm.cv, (unsigned)kLossThreads);
-    const unsigned gf = g / q * q;
-    if (gf > 0 && (g - gf) * 25u <= g) {
-      cls_sums_flat_kernel<6, 4><<<gf, kLossThreads, fsmem, st>>>(segs, prm);
-      RN_CUDA_CHECK_LAUNCH("rn_cls_sums(flat)");
-      return RN_OK;
-    }
+    // by bytes in flight.  bf16x8 units carry twice the classes (and accumulators): four loads in flight.
+#define RN_SUMS_FLAT(U, BF)                                                                                      \
+    do {                                                                                                           \
+      const size_t fsmem = (size_t)kLossThreads * (BF ? 16 : 8) * sizeof(double);                                  \
+      unsigned g = persistent_grid(cls_sums_flat_kernel<U, 4, BF>, kLossThreads, fsmem,                            \
+                                   (total_rows * prm.cv + 3) / 4);                                                 \
+      const unsigned q = (unsigned)prm.cv / gcd_u((unsigned)prm.cv, (unsigned)kLossThreads);                       \
+      const unsigned gf = g / q * q;                                                                               \
+      if (gf > 0 && (g - gf) * 25u <= g) {                                                                         \
+        cls_sums_flat_kernel<U, 4, BF><<<gf, kLossThreads, fsmem, st>>>(segs, prm);                                \
+        RN_CUDA_CHECK_LAUNCH("rn_cls_sums(flat)");                                                                 \
+        return RN_OK;                                                                                              \
+      }                                                                                                            \
+    } while (0)
+    if (bf16) RN_SUMS_FLAT(4, true); else RN_SUMS_FLAT(6, false);
+#undef RN_SUMS_FLAT
   }
+  RN_REQUIRE(!bf16, RN_ERR_UNSUPPORTED, "rn_cls_sums: bf16 logits: no launch configuration for this shape");
   if (!dense_labels && vec4 && g_fast_kernels && rows32 && prm.cv <= 256) {
     prm.ry = 256 / prm.cv > 0 ? 256 / prm.cv : 1;
     const int fthreads = prm.cv * prm.ry;
@@ -1506,9 +1549,9 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
   const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_kernels && fits32 &&
                        num_classes <= 2048;
-  RN_REQUIRE(!bf16 || (fast_ok && !dice && base != RN_CLS_NONE && num_classes % 8 == 0), RN_ERR_UNSUPPORTED,
+  RN_REQUIRE(!bf16 || (fast_ok && (dice || base != RN_CLS_NONE) && num_classes % 8 == 0), RN_ERR_UNSUPPORTED,
              "bfloat16 logits need the fast kernel: compact labels, C %% 8 == 0, focal (focus 2) / BCE / balanced BCE "
-             "without dice");
+             "and/or dice");
   if (fast_ok) {
     FastParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -1598,8 +1641,8 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
   fp.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(d_loss_workspace) + 256);
   RN_REQUIRE(logits_dtype == RN_DTYPE_F32 || logits_dtype == RN_DTYPE_BF16, RN_ERR_BAD_ARG, "unknown logits_dtype");
   const bool bf16 = logits_dtype == RN_DTYPE_BF16;
-  RN_REQUIRE(!bf16 || (num_classes % 8 == 0 && !(mode & RN_CLS_DICE_FLAG) && (mode & 15) != RN_CLS_NONE),
-             RN_ERR_UNSUPPORTED, "bfloat16 logits need C %% 8 == 0 and a mode without dice");
+  RN_REQUIRE(!bf16 || num_classes % 8 == 0,
+             RN_ERR_UNSUPPORTED, "bfloat16 logits need C %% 8 == 0");
   fp.num_classes = num_classes;
   fp.cv = num_classes / (bf16 ? 8 : 4);
   fp.bf16 = bf16 ? 1 : 0;

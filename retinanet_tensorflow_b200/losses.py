@@ -103,7 +103,7 @@ def _class_stats(labels, logits=None):
         ws, n = _ws(c, labels.device)
         seg = _lib.rows_of([rows])
         _lib.call('rn_cls_sums', C.byref(seg), c, C.byref(_lib.maps_of([logits.reshape(rows, c)])),
-                  C.byref(_lib.maps_of([labels.reshape(rows, c)])), 1, _lib.ptr(stats), _lib.ptr(ws), n,
+                  C.byref(_lib.maps_of([labels.reshape(rows, c)])), 1, _lib.RN_DTYPE_F32, _lib.ptr(stats), _lib.ptr(ws), n,
                   _lib.stream_ptr())
     h = _lib.RN_STATS_HEADER
     return stats, stats[h:h + c], stats[h + c:h + 2 * c], stats[h + 2 * c:h + 3 * c]

@@ -237,7 +237,7 @@ class DenseHeadPath(object):
         m_dlogits, m_dreg, dt = self._grad_buffers(logits_t, want_grad)
         if self.mode & _lib.RN_CLS_DICE_FLAG:
             self._stage('cls_sums', lambda: _lib.call(
-                'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
+                'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, dt,
                 _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
             self._allreduce('dice_sums')
         self._stage('cls_loss', lambda: _lib.call(
@@ -273,7 +273,7 @@ class DenseHeadPath(object):
         m_dlogits, m_dreg, dt = self._grad_buffers(logits_t, want_grad)
         if self.mode & _lib.RN_CLS_DICE_FLAG:
             self._stage('cls_sums', lambda: _lib.call(
-                'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0,
+                'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, dt,
                 _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
             self._allreduce('dice_sums')
         self._stage('cls_loss', lambda: _lib.call(
@@ -303,13 +303,14 @@ class DenseHeadPath(object):
 
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
-        if isinstance(scores, torch.Tensor) and scores.dtype == torch.bfloat16:
-            scores = scores.float()   # the standalone select kernel is float32; bf16 is fused-path only
-        m_scores, _ = self._maps(scores, self.num_classes)
+        m_scores, scores_t = self._maps(scores, self.num_classes, self._LOGIT_DTYPES)
+        first = scores_t[0] if isinstance(scores_t, (list, tuple)) else scores_t
+        fmt = (_lib.RN_SCORES_LOGITS if scores_are_logits else 0) | \
+            (_lib.RN_SCORES_BF16 if first.dtype == torch.bfloat16 else 0)
         m_reg, _ = self._maps(regression, 4)
         self._stage('select', lambda: _lib.call(
             'rn_decode_select', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_scores),
-            int(scores_are_logits), C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level,
+            fmt, C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level,
             self.capacity, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
             _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self.status), _lib.ptr(self._sel_ws),
             self._sel_ws_bytes, _lib.stream_ptr()))
