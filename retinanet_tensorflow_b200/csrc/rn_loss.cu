@@ -1454,8 +1454,9 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
       unsigned g = persistent_grid(cls_sums_flat_kernel<U, 4, BF>, kLossThreads, fsmem,                            \
                                    (total_rows * prm.cv + 3) / 4);                                                 \
       const unsigned q = (unsigned)prm.cv / gcd_u((unsigned)prm.cv, (unsigned)kLossThreads);                       \
-      const unsigned gf = g / q * q;                                                                               \
-      if (gf > 0 && (g - gf) * 25u <= g) {                                                                         \
+      unsigned gf = g / q * q;                                                                                     \
+      if (BF && gf == 0) gf = q;   /* bf16 has no other kernel: a few idle CTAs instead of a fallback */            \
+      if (gf > 0 && (BF || (g - gf) * 25u <= g)) {                                                                 \
         cls_sums_flat_kernel<U, 4, BF><<<gf, kLossThreads, fsmem, st>>>(segs, prm);                                \
         RN_CUDA_CHECK_LAUNCH("rn_cls_sums(flat)");                                                                 \
         return RN_OK;                                                                                              \
