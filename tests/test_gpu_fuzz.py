@@ -16,3 +16,8 @@ def test_fuzz_slice():
 def test_fuzz_loss_slice():
     import fuzz_loss
     assert fuzz_loss.run(cases=40, seed=1) == 40
+
+
+def test_fuzz_select_slice():
+    import fuzz_select
+    assert fuzz_select.run(cases=30, seed=1) == 30
