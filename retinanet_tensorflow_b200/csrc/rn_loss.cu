@@ -284,7 +284,8 @@ __device__ __forceinline__ float focal_neg_fast(float x, float eps, float cg, fl
 __device__ __forceinline__ float focal_neg_bulk(float x, float eps, float cg, float& grad, float& pq) {
   // x <= -0.70: the rounding error of x*log2(e) adds at most |x| * 6e-8 relative to e (3e-7 at
   // the prior logit), so the exact-product correction of exp_neg_fast is not needed here.
-  const float e = ex2_approx(fminf(x * -1.44269502163e+00f, 126.0f));
+  // (no clamp: for very negative x the exponential overflows to +inf, rcp.approx(inf) = 0, and p = 0 is exact)
+  const float e = ex2_approx(x * -1.44269502163e+00f);
   const float p = rcp_approx(1.0f + e);
   const float q = 1.0f - p;
   const float w = 1.0f - q;
