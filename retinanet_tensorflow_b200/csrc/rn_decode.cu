@@ -369,27 +369,31 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
     // 1b) The fused loss+select pass appends one entry per firing float4 UNIT, so an anchor with
     // several classes above the threshold appears more than once: keep its best entry (max
     // probability, then lowest class == the first argmax of utils.py:185-186).
+    // Every entry decides for itself whether another entry of its anchor beats it (reads only), and the marks are
+    // written after a barrier -- a group is at most C/4 entries, so the scan is short.
     bool mine = false;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned a = (unsigned)key[i];
-      if (i > 0 && (unsigned)key[i - 1] == a) continue;   // not the head of its group
-      int best = i, j = i + 1;
-      float bs = prm.ws_score[base + pos[i]];
-      int bc = prm.ws_class[base + pos[i]];
-      for (; j < n && (unsigned)key[j] == a; ++j) {
-        const float sj = prm.ws_score[base + pos[j]];
-        const int cj = prm.ws_class[base + pos[j]];
-        if (sj > bs || (sj == bs && cj < bc)) {
-          best = j;
-          bs = sj;
-          bc = cj;
+    for (int c0 = 0; c0 < n; c0 += blockDim.x) {   // same trip count for every thread
+      const int i = c0 + (int)threadIdx.x;
+      bool drop = false;
+      if (i < n) {
+        const unsigned a = (unsigned)key[i];
+        const float si = prm.ws_score[base + pos[i]];
+        const int ci = prm.ws_class[base + pos[i]];
+        for (int t = i - 1; t >= 0 && (unsigned)key[t] == a && !drop; --t) {   // an earlier entry also wins full ties
+          const float st = prm.ws_score[base + pos[t]];
+          drop = st > si || (st == si && prm.ws_class[base + pos[t]] <= ci);
+        }
+        for (int t = i + 1; t < n && (unsigned)key[t] == a && !drop; ++t) {
+          const float st = prm.ws_score[base + pos[t]];
+          drop = st > si || (st == si && prm.ws_class[base + pos[t]] < ci);
         }
       }
-      if (j > i + 1) {
+      __syncthreads();
+      if (drop) {
+        key[i] |= 1ull << 62;   // dropped duplicate: sorts behind every kept entry
         mine = true;
-        for (int t = i; t < j; ++t)
-          if (t != best) key[t] |= 1ull << 62;   // dropped duplicate: sorts behind every kept entry
       }
+      __syncthreads();
     }
     if (__syncthreads_or(mine)) {
       bitonic_sort_pairs(key, pos, n_pad);

@@ -40,6 +40,23 @@ def main():
             augmentation.flip_compact(path.pyr, 2, path.label, path.deltas)
             torch.cuda.synchronize()
             path.check_status(ignore=12)
+    # bfloat16 logits in every kernel that takes them (fused loss + select, dice sums, standalone select), and dense
+    # firing into a small candidate list (warp-aggregated appends, full lists, overflow flag)
+    wl = synthetic.WORKLOADS['voc']
+    wl = synthetic.Workload('voc24', wl.config, 160, 192, 24, wl.max_gt, 2)
+    boxes, cls, counts = synthetic.gt_batch(wl, 2)
+    gt = [torch.from_numpy(x).cuda() for x in (boxes, cls, counts)]
+    for mode in ('focal', 'bce_dice'):
+        path = DenseHeadPath((wl.image_h, wl.image_w), 24, 2, wl.max_gt, cls_mode=mode, capacity=64, score_thr=0.05,
+                             process_group=False)
+        path.assign(*gt)
+        logits, regs = synthetic.head_outputs(path.label, path.deltas, 24, seed=2, device='cuda')
+        l16 = (logits + 3.0).bfloat16()
+        path.step(*gt, l16, regs)
+        path.detect(l16, regs)
+        path.step(*gt, logits + 3.0, regs)
+        torch.cuda.synchronize()
+        path.check_status(ignore=12)
     b, c = synthetic.gt_for_image(synthetic.WORKLOADS['shapes'], 0)
     dataset.build_labels([128, 160], c, b, build_levels(), 3)
     rng = np.random.default_rng(0)
