@@ -206,10 +206,26 @@ class DenseHeadPath(object):
         return fn() if self.stage_hook is None else self.stage_hook(name, fn)
 
     # ---- stage 1: assignment + encoding (dataset.build_labels) ------------------------------
-    def assign(self, gt_boxes, gt_classes, gt_counts):
+    def _second_half(self, maps, bytes_per_anchor, images):
+        """The per-level pointers of `maps` advanced past the first `images` images of every level."""
+        out = _lib.Maps()
+        for l, (h, w, a) in enumerate(level_shapes(self.pyr)):
+            out.p[l] = maps.p[l] + images * h * w * a * bytes_per_anchor if maps.p[l] else None
+        return out
+
+    def assign(self, gt_boxes, gt_classes, gt_counts, with_flip=False):
         """gt_boxes f32 [B, max_gt, 4], gt_classes i32 [B, max_gt], gt_counts i32 [B] (device).
-        Fills self.matched / label / deltas and the label statistics."""
+        Fills self.matched / label / deltas and the label statistics.
+
+        with_flip=True builds the reference's `[orig, flipped]` sample (dataset.py:182-204) on the
+        device: the ground truth holds batch/2 images, they are assigned into the first half of every
+        level and their horizontally flipped label maps (augmentation.py:5-22) into the second half,
+        so that images b and b + batch/2 are a flip pair (the caller flips the pixels)."""
         B = self.batch
+        if with_flip:
+            if B % 2:
+                raise ValueError('with_flip needs an even batch (it holds [orig, flipped])')
+            B //= 2
         if tuple(gt_boxes.shape) != (B, self.max_gt, 4) or gt_boxes.dtype != torch.float32:
             raise ValueError('gt_boxes must be float32 [%d, %d, 4]' % (B, self.max_gt))
         if tuple(gt_classes.shape) != (B, self.max_gt) or gt_classes.dtype != torch.int32:
@@ -223,6 +239,17 @@ class DenseHeadPath(object):
             self.max_gt, self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched),
             C.byref(self._m_label), C.byref(self._m_deltas), C.byref(self._m_iou), _lib.ptr(self.stats),
             _lib.ptr(self.status), _lib.stream_ptr()))
+        if with_flip:
+            st = _lib.stream_ptr()
+            none = _lib.Maps()
+            _lib.call('rn_flip_labels', C.byref(self.pyr), B, C.byref(self._m_label), C.byref(self._m_deltas),
+                      C.byref(self._second_half(self._m_label, 4, B)),
+                      C.byref(self._second_half(self._m_deltas, 16, B)), st)
+            for m in (self._m_matched, self._m_iou):   # 4-byte payloads: the label slot of the same kernel moves them
+                if m.p[0]:
+                    _lib.call('rn_flip_labels', C.byref(self.pyr), B, C.byref(m), C.byref(none),
+                              C.byref(self._second_half(m, 4, B)), C.byref(none), st)
+            self.stats[:_lib.RN_STATS_HEADER + self.num_classes] *= 2.0   # a flip keeps every count
         self._allreduce('counts')
         return self.label, self.deltas
 

@@ -188,3 +188,51 @@ def test_non_finite_gt_is_flagged():
     assert int(path.status.item()) & _lib.RN_FLAG_IOU_RANGE
     with pytest.raises(AssertionError):
         path.check_status()
+
+
+def test_orig_and_flip_batch_on_device():
+    """dataset.py:182-204: the reference trains on [orig, flipped] pairs.  assign(with_flip=True) builds
+    the pair's label maps on the device; labels, statistics, losses and gradients of the 2-image batch
+    must equal the oracle's on [labels, augmentation.flip(labels)] (SURVEY config 1: Shapes, batch 2)."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['shapes']
+    ref = helpers.oracle_labels_batch(wl, 1)
+    both = {k: {} for k in ('cls', 'reg', 'mask')}
+    for pn in ref['cls']:
+        sample = {'detection': {'classifications': {pn: ref['cls'][pn][0]}, 'regressions': {pn: ref['reg'][pn][0]}},
+                  'trainable_masks': {pn: ref['mask'][pn][0]}}
+        fl = oracle.flip(sample)
+        both['cls'][pn] = np.stack([ref['cls'][pn][0], fl['detection']['classifications'][pn]], 0)
+        both['reg'][pn] = np.stack([ref['reg'][pn][0], fl['detection']['regressions'][pn]], 0)
+        both['mask'][pn] = np.stack([ref['mask'][pn][0], fl['trainable_masks'][pn]], 0)
+    cls = helpers.merge_levels(both['cls'], 1)
+    mask = helpers.merge_levels(both['mask'])
+    reg = helpers.merge_levels(both['reg'], 1)
+    boxes, classes, counts = synthetic.gt_batch(wl, 1)
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 2, wl.max_gt, cls_mode='bce_dice', keep_iou=True,
+                         process_group=False)
+    path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda(),
+                with_flip=True)
+    torch.cuda.synchronize()
+    path.check_status()
+    np.testing.assert_array_equal(path.label.cpu().numpy(), helpers.compact_labels(cls, mask))
+    helpers.assert_close(path.deltas.cpu().numpy(), reg, rtol=1e-5, atol=1e-7, what='deltas [orig, flip]')
+    # matched index and max IoU travel with their anchors
+    m_lv, i_lv = path.per_level(path.matched), path.per_level(path.iou_max)
+    for pn in path.names:
+        assert torch.equal(m_lv[pn][1], torch.flip(m_lv[pn][0], dims=[1]))
+        assert torch.equal(i_lv[pn][1], torch.flip(i_lv[pn][0], dims=[1]))
+    logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=3, device='cuda')
+    out = path.loss(logits, regs).cpu().numpy()
+    x, r = logits.cpu().numpy(), regs.cpu().numpy()
+    labels = oracle.Detection(oracle.Classification(None, cls[mask]), reg[mask], None)
+    preds = oracle.Detection(oracle.Classification(x[mask], oracle.sigmoid(x[mask])), r[mask], None)
+    cl, rl = oracle.loss(labels, preds, mode='bce_dice')
+    fg = oracle.classmap_decode(cls[mask]).fg_mask
+    np.testing.assert_allclose(out[:2], [cl, rl], rtol=1e-5)
+    assert out[2] == fg.sum() and out[3] == mask.sum()
+    g_ref = np.zeros_like(x)
+    g_ref[mask] = oracle.classification_loss_grad(cls[mask], x[mask], fg, mode='bce_dice')
+    helpers.assert_close(path.dlogits.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max(), what='dlogits')
