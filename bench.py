@@ -197,7 +197,7 @@ def anchors_of(wl):
 
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -206,7 +206,20 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.p = None
 
+    def ready(self):
+        """True once nvidia-smi has printed its first sample (it can take seconds on an 8-GPU box)."""
+        try:
+            return self.p is None or os.path.getsize(self.f.name) > 0
+        except OSError:
+            return True
+
+    def _kill(self):
+        if self.p is not None and self.p.poll() is None:
+            self.p.kill()
+
     def start(self):
+        import atexit
+        atexit.register(self._kill)   # never leave an orphan nvidia-smi behind, whatever happens to the bench
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q,
                                        '--format=csv,noheader,nounits', '-lms', '50'], stdout=self.f,
@@ -214,7 +227,11 @@ class ClockSampler(object):
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples taken in the wall-clock window [t0, t1] (the
+        warm-up + timed steps).  nvidia-smi is started long before that window, because on an 8-GPU box it
+        needs more than the timed region to print its first line."""
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.p is None:
             return out
@@ -226,6 +243,17 @@ class ClockSampler(object):
         self.f.flush()
         rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
+        if t0 is not None:
+            inside = []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                except ValueError:
+                    continue
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    inside.append(r)
+            out['window'] = 'warm-up + timed steps' if inside else 'whole process (no sample fell inside the timed window)'
+            rows = inside or rows
         sm, reasons, mx, pw = [], set(), None, []
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in rows:
@@ -305,6 +333,12 @@ def run_b200(args):
                           n_img, wl.name),
             'stage_seconds_per_image': stages}
 
+    # nvidia-smi starts now (it needs seconds to come up on an 8-GPU box); only the samples inside the warm-up +
+    # timed window are used
+    sampler = ClockSampler('GPU-' + str(torch.cuda.get_device_properties(dev).uuid))
+    if rank == 0:
+        sampler.start()
+
     # ---- inputs resident in HBM
     path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, cls_mode=args.cls_mode,
                          capacity=8192, process_group=None if world > 1 else False, device=dev,
@@ -328,6 +362,7 @@ def run_b200(args):
     if args.mode == 'infer':
         # BASELINE configs[3]: inference post-processing only (standalone select -> top-k -> NMS)
         path.topk_per_level = args.topk
+        t_load0 = time.time()
         for _ in range(args.warmup):
             path.detect(logits, regs)
         barrier()
@@ -338,6 +373,7 @@ def run_b200(args):
         b.record()
         barrier()
         ms = a.elapsed_time(b)
+        clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
         if rank == 0:
             peak, _ = measured_peaks()
             sel_bytes = batch * path.anchors * 4 * wl.num_classes
@@ -345,7 +381,7 @@ def run_b200(args):
                 'metric': 'images/sec (decode + score>0.5 + top-%d per level + per-class NMS IoU 0.5)' % args.topk,
                 'value': world * batch * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(wl, args, batch),
+                'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(wl, args, batch), 'clocks': clocks,
                 'alg_bytes_per_step': sel_bytes, 'frac_of_hbm_whole_step': sel_bytes / (ms / args.steps * 1e-3) / 1e9 / peak,
                 'detections': int(path.det_count.sum().item()), 'candidates': int(path.cand_count.sum().item())}))
         return 0
@@ -379,12 +415,22 @@ def run_b200(args):
         else:
             path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
 
+    # extra untimed warm-up until the clock sampler delivers (rank 0 decides, every rank runs the same steps)
+    warmup_extra = 0
+    for _ in range(200):
+        ready = torch.tensor([1 if (rank != 0 or sampler.ready()) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(ready, src=0)
+        if int(ready.item()):
+            break
+        for _ in range(25):
+            one_step()
+        warmup_extra += 25
+        torch.cuda.synchronize()
+    t_load0 = time.time()
     for _ in range(args.warmup):
         one_step()
     barrier()
-    sampler = ClockSampler('GPU-' + str(torch.cuda.get_device_properties(dev).uuid))
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.lib.rn_launch_count()
     record['on'] = True
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -404,7 +450,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         launches = (_lib.lib.rn_launch_count() - l0) // 10 * args.steps
     record['on'] = False
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_load0, time.time()) if rank == 0 else None
     ms = start.elapsed_time(end)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -484,7 +530,8 @@ def run_b200(args):
         value = world * batch * args.steps / (ms_total * 1e-3)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'warmup': args.warmup, 'warmup_extra': warmup_extra, 'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32' if args.logits_dtype == 'f32' else 'f32 math on bf16 logits',
             'data': 'synthetic',
             'config': workload_config(wl, args, batch),
