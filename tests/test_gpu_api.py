@@ -359,3 +359,43 @@ def test_dormant_metrics():
     pz, zz = oracle.sigmoid(x) > 0.5, z > 0.5
     want_ci = np.mean([((zz == c) & (pz == c)).sum() / max(((zz == c) | (pz == c)).sum(), 1) for c in (False, True)])
     assert abs(ci - want_ci) < 1e-6
+
+
+def test_label_path_is_reentrant_from_four_threads():
+    """dataset.py:231 maps build_labels over <= 4 tf.data threads: the library keeps no mutable global
+    state, so concurrent calls (ctypes releases the GIL) give the same labels as sequential ones."""
+    import threading
+    import torch
+    from retinanet_tensorflow_b200 import dataset, synthetic
+    from retinanet_tensorflow_b200.levels import build_levels
+    wl = synthetic.WORKLOADS['voc']
+    levels = build_levels()
+    images = [synthetic.gt_for_image(wl, i) for i in range(12)]
+    size = [wl.image_h, wl.image_w]
+
+    def labels(i):
+        b, c = images[i]
+        cls, reg, mask = dataset.build_labels(size, c, b, levels, wl.num_classes)
+        return [x[pn].clone() for x in (cls, reg, mask) for pn in levels]
+
+    want = [labels(i) for i in range(len(images))]
+    got = [None] * len(images)
+    errors = []
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            for i in range(k, len(images), 4):
+                got[i] = labels(i)
+            torch.cuda.synchronize()
+        except Exception as err:   # surfaced below: a thread must not fail silently
+            errors.append(err)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for w, g in zip(want, got):
+        assert all(torch.equal(a, b) for a, b in zip(w, g))
