@@ -197,8 +197,16 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
       d.x = fdiv(fsub(t.x, cy), h);   // shifts, dataset.py:108
       d.y = fdiv(fsub(t.y, cx), w);
       const float rh = fdiv(t.z, h), rw = fdiv(t.w, w);   // scales, dataset.py:110
-      d.z = rh > 0.f ? log_fast(rh) : logf(rh);           // log(scales), dataset.py:112
-      d.w = rw > 0.f ? log_fast(rw) : logf(rw);
+      d.z = log_fast(rh);                                 // log(scales), dataset.py:112
+      d.w = log_fast(rw);
+      // log_fast is for positive normal finite arguments (sign 0, exponent field 1..254); anything else -- a
+      // zero-area, denormal-sized, negative or non-finite box -- takes libm in one shared rare branch
+      const bool nh = (unsigned)(__float_as_int(rh) - 0x00800000) < 0x7f000000u;
+      const bool nw = (unsigned)(__float_as_int(rw) - 0x00800000) < 0x7f000000u;
+      if (!(nh && nw)) {
+        if (!nh) d.z = logf(rh);
+        if (!nw) d.w = logf(rw);
+      }
     }
     reinterpret_cast<int32_t*>(prm.matched.p[l])[row] = matched;
     reinterpret_cast<int32_t*>(prm.label.p[l])[row] = lab;

@@ -236,3 +236,35 @@ def test_orig_and_flip_batch_on_device():
     g_ref = np.zeros_like(x)
     g_ref[mask] = oracle.classification_loss_grad(cls[mask], x[mask], fg, mode='bce_dice')
     helpers.assert_close(path.dlogits.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max(), what='dlogits')
+
+
+def test_denormal_and_zero_sized_ground_truth_boxes():
+    """A box whose height is a float32 denormal (and one of zero height) still goes through the
+    reference's arithmetic: IEEE division, log of a denormal / of zero (-inf) in the encoded sizes."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.Workload('tiny', 1, 96, 128, 3, 4, 1)
+    tiny = np.float32(1e-40)
+    assert 0 < tiny < np.finfo(np.float32).tiny
+    cases = [np.array([[0.25, 0.25, np.float32(0.25) + tiny, 0.75], [0.1, 0.2, 0.6, 0.7]], np.float32),
+             np.array([[0.5, 0.25, 0.5, 0.75], [0.1, 0.2, 0.6, 0.7]], np.float32)]
+    for boxes in cases:
+        classes = np.array([1, 2], np.int32)
+        gb = np.zeros((1, 4, 4), np.float32)
+        gb[0, :2] = boxes
+        gc = np.zeros((1, 4), np.int32)
+        gc[0, :2] = classes
+        path = DenseHeadPath((wl.image_h, wl.image_w), 3, 1, 4, process_group=False)
+        path.assign(torch.from_numpy(gb).cuda(), torch.from_numpy(gc).cuda(), torch.tensor([2], dtype=torch.int32).cuda())
+        torch.cuda.synchronize()
+        with np.errstate(all='ignore'):
+            o_cls, o_reg, o_mask = oracle.build_labels(np.array([96, 128], np.int32), classes, boxes, oracle.build_levels(), 3)
+        lab = path.per_level(path.label)
+        dl = path.per_level(path.deltas, (4,))
+        for pn in path.names:
+            np.testing.assert_array_equal(lab[pn][0].cpu().numpy(), helpers.compact_labels(o_cls[pn], o_mask[pn]))
+            got, want = dl[pn][0].cpu().numpy(), o_reg[pn]
+            assert np.array_equal(np.isneginf(got), np.isneginf(want))
+            fin = np.isfinite(want)
+            helpers.assert_close(got[fin], want[fin], rtol=1e-5, atol=1e-7, what='deltas ' + pn)
