@@ -141,3 +141,36 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'rn_oracle' not in text and 'import oracle' not in text, f
+
+
+def test_pyramid_constants_property():
+    """rn_pyramid_build (host C) against the oracle for random image sizes and both anchor-size modes:
+    grids, anchor sizes and the float32 linspace constants bit for bit (hypothesis, 60 examples)."""
+    hyp = pytest.importorskip('hypothesis')
+    from hypothesis import strategies as st
+    from retinanet_tensorflow_b200._pyramid import pyramid_for
+    from retinanet_tensorflow_b200.levels import build_levels
+    levels = build_levels()
+
+    @hyp.settings(max_examples=60, deadline=None, database=None)
+    @hyp.given(st.integers(9, 2100), st.integers(9, 2100), st.sampled_from(['tf1_int_trunc', 'float']))
+    def check(h, w, mode):
+        pyr = pyramid_for((h, w), levels, mode)
+        off = 0
+        for l, pn in enumerate(levels):
+            lv = pyr.level[l]
+            grid = oracle.grid_size_for(np.array((h, w), np.int32), 2 ** int(pn[-1]))
+            assert (lv.grid_h, lv.grid_w) == (int(grid[0]), int(grid[1]))
+            sizes = oracle.anchor_size_normalised(levels[pn].anchor_sizes, np.array((h, w), np.int32), mode)
+            np.testing.assert_array_equal(np.array(lv.anchor_h[:9], np.float32), sizes[:, 0])
+            np.testing.assert_array_equal(np.array(lv.anchor_w[:9], np.float32), sizes[:, 1])
+            y, x = oracle._grid_axes(grid)
+            gy = (np.float32(lv.y0) + (np.float32(lv.y_step) * np.arange(lv.grid_h, dtype=np.float32))).astype(np.float32)
+            gx = (np.float32(lv.x0) + (np.float32(lv.x_step) * np.arange(lv.grid_w, dtype=np.float32))).astype(np.float32)
+            np.testing.assert_array_equal(gy, y)
+            np.testing.assert_array_equal(gx, x)
+            assert lv.anchor_offset == off
+            off += lv.grid_h * lv.grid_w * 9
+        assert pyr.anchors_per_image == off
+
+    check()
