@@ -67,13 +67,15 @@ def oracle_assign(case):
     import rn_oracle as oracle
     levels = oracle.build_levels()
     size = np.array([case['h'], case['w']], np.int32)
-    out = {k: {} for k in ('cls', 'mask', 'idx', 'iou')}
+    out = {k: {} for k in ('cls', 'mask', 'idx', 'iou', 'reg')}
     for pn in levels:
         c, r, m, idx, iou = oracle.level_labels(size, case['classes'], case['boxes'], levels[pn], 2 ** int(pn[-1]),
                                                 case['c'], anchor_size_mode=case['mode'], return_aux=True)
         out['cls'][pn], out['mask'][pn], out['idx'][pn], out['iou'][pn] = c[None], m[None], idx[None], iou[None]
+        out['reg'][pn] = r[None]
     lab = helpers.compact_labels(helpers.merge_levels(out['cls'], 1), helpers.merge_levels(out['mask']))
-    return (case['seed'], lab, helpers.merge_levels(out['idx']).astype(np.int32), helpers.merge_levels(out['iou']))
+    return (case['seed'], lab, helpers.merge_levels(out['idx']).astype(np.int32), helpers.merge_levels(out['iou']),
+            helpers.merge_levels(out['reg'], 1))
 
 
 def gpu_assign(case):
@@ -84,7 +86,7 @@ def gpu_assign(case):
                          process_group=False)
     path.assign(torch.from_numpy(case['boxes'][None]).cuda(), torch.from_numpy(case['classes'][None]).cuda(),
                 torch.tensor([n], dtype=torch.int32).cuda())
-    return path.label.cpu().numpy(), path.matched.cpu().numpy(), path.iou_max.cpu().numpy()
+    return path.label.cpu().numpy(), path.matched.cpu().numpy(), path.iou_max.cpu().numpy(), path.deltas.cpu().numpy()
 
 
 def make_nms_case(seed):
@@ -130,8 +132,15 @@ def run(cases, seed, workers):
         a_ref, n_ref = a_ref.get(), n_ref.get()
     bad = 0
     stats = {'pos': 0, 'ign': 0, 'anchors': 0, 'kept': 0}
-    for case, (lab, idx, iou), (_, o_lab, o_idx, o_iou) in zip(a_cases, a_gpu, a_ref):
+    for case, (lab, idx, iou, reg), (_, o_lab, o_idx, o_iou, o_reg) in zip(a_cases, a_gpu, a_ref):
         ok = np.array_equal(lab, o_lab) and np.array_equal(idx, o_idx) and np.array_equal(iou, o_iou)
+        # encoded deltas (tolerance claim: 1e-5 relative + 1e-7): same non-finite pattern, close elsewhere
+        fin = np.isfinite(o_reg)
+        if not (np.array_equal(fin, np.isfinite(reg)) and
+                np.all(np.abs(reg[fin] - o_reg[fin]) <= 1e-5 * np.abs(o_reg[fin]) + 1e-7)):
+            bad += 1
+            print('DELTAS MISMATCH seed', case['seed'], 'size', case['h'], case['w'],
+                  float(np.abs(reg[fin] - o_reg[fin]).max()) if fin.any() else None)
         stats['pos'] += int((o_lab >= 0).sum())
         stats['ign'] += int((o_lab == -2).sum())
         stats['anchors'] += o_lab.shape[0]
