@@ -83,6 +83,7 @@ class DenseHeadPath(object):
         self.stage_hook = None  # optional callable(stage_name, thunk) -> thunk(); bench.py times stages with it
         self._side = None        # side stream for the detection tail (step(overlap_detect=True))
         self._side_done = None
+        self._stats_fin = None   # statistics snapshot for a loss that is finished on the side stream
         self.pyr = pyramid_for(self.image_size, self.levels, anchor_size_mode, self.names)
         self.anchors = int(self.pyr.anchors_per_image)
         self.rows_total = self.batch * self.anchors
@@ -182,7 +183,7 @@ class DenseHeadPath(object):
         return self.group is not False and d.is_available() and d.is_initialized() and d.get_world_size(
             self.group if self.group is not None else None) > 1
 
-    def _allreduce(self, phase):
+    def _allreduce(self, phase, stats=None):
         """Sum one slice of the stats vector over the ranks ('counts' | 'dice_sums' | 'loss_sums').
         process_group=False disables.  exchange='peer' uses rn_stats_exchange (this library's kernel
         over NVLink peer memory), 'nccl' torch.distributed.all_reduce, 'auto' tries peer first."""
@@ -197,10 +198,11 @@ class DenseHeadPath(object):
                 import warnings
                 warnings.warn('peer-memory exchange unavailable (%s); using NCCL all-reduce' % (err,))
                 self.exchange = 'nccl'
+        stats = self.stats if stats is None else stats
         if self._peer is not None and self.exchange != 'nccl':
-            self._peer.all_reduce(self.stats, phase, self.status)
+            self._peer.all_reduce(stats, phase, self.status)
         else:
-            dist.all_reduce_sum(self.stats[dist.slices(self.num_classes)[phase]], self.group)
+            dist.all_reduce_sum(stats[dist.slices(self.num_classes)[phase]], self.group)
 
     def _stage(self, name, fn):
         return fn() if self.stage_hook is None else self.stage_hook(name, fn)
@@ -284,7 +286,17 @@ class DenseHeadPath(object):
         return bool(_lib.lib.rn_fused_select_supported(self.num_classes, self.mode, self.focus, C.byref(self.rows))) \
             and 0.0 < self.score_thr < 1.0
 
-    def loss_and_select(self, logits, regression, want_grad=True, finalize=True):
+    def _can_defer_loss(self):
+        """The loss-sum exchange + finalize may leave the critical path (side stream) unless the exchange is an
+        NCCL collective, whose cross-stream ordering is torch's business, not ours."""
+        return not self._multi_rank() or (self._peer is not None and self.exchange != 'nccl')
+
+    def _finish_loss(self, stats):
+        self._allreduce('loss_sums', stats)
+        _lib.call('rn_loss_finalize', self.num_classes, self.mode, _lib.ptr(stats), _lib.ptr(self.loss_out),
+                  _lib.stream_ptr())
+
+    def loss_and_select(self, logits, regression, want_grad=True, finalize=True, defer_loss=False):
         """`loss()` and `select()` on the same logits with the [rows, C] tensor read ONCE: the
         focal kernel also pre-selects the anchors whose best class probability exceeds score_thr
         (training step that also produces detections, train.py:218-220 + 68-75).
@@ -312,8 +324,14 @@ class DenseHeadPath(object):
             'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
             C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
             self._huber_ws.numel(), st))
-        self._allreduce('loss_sums')
-        _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
+        if defer_loss:
+            # snapshot of the statistics: the next step's assignment zeroes self.stats while the side stream still
+            # needs this step's sums (step(overlap_detect=True) finishes the loss there)
+            if self._stats_fin is None:
+                self._stats_fin = torch.empty_like(self.stats)
+            self._stats_fin.copy_(self.stats)
+        else:
+            self._finish_loss(self.stats)
         if finalize:
             self.select_finalize(regression)
         return self.loss_out, self.cand_count
@@ -364,9 +382,10 @@ class DenseHeadPath(object):
 
         overlap_detect=True puts the latency-bound tail (candidate finalize + NMS, one CTA per
         image) on a side stream so that it overlaps the next step's assignment and loss kernels;
-        events keep the select workspace from being overwritten early.  Detections are then valid
-        after `join()` (or a device synchronize); losses and gradients are on the current stream
-        as always."""
+        events keep the select workspace from being overwritten early.  The loss-sum exchange and
+        the final normalisation (`loss_out`) ride on the side stream too (unless the exchange is an
+        NCCL collective).  Detections and `loss_out` are then valid after `join()` (or a device
+        synchronize); gradients are on the current stream as always."""
         self.assign(gt_boxes, gt_classes, gt_counts)
         if not (fused and self.fused_select_supported()):
             self.join()
@@ -378,17 +397,21 @@ class DenseHeadPath(object):
         if self._side_done is not None:
             main.wait_event(self._side_done)   # previous tail has consumed the select workspace
             self._side_done = None
-        self.loss_and_select(logits, regression, finalize=False)
         if not overlap_detect:
+            self.loss_and_select(logits, regression, finalize=False)
             self.select_finalize(regression)
             self.nms()
             return self.loss_out, self.det_count
+        defer = self._can_defer_loss()
+        self.loss_and_select(logits, regression, finalize=False, defer_loss=defer)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device, priority=-1)  # small CTAs first
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(self._side):
             self._side.wait_event(ready)
+            if defer:   # loss-sum exchange + finalize: nothing on the main stream waits for them
+                self._finish_loss(self._stats_fin)
             self.select_finalize(regression)
             self.nms()
             self._side_done = torch.cuda.Event()

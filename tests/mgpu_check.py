@@ -31,6 +31,19 @@ def run(wl, first, count, group, mode, logits=None, regs=None):
                                               device='cuda')
     path.step(gb, gc, gn, logits, regs)
     torch.cuda.synchronize()
+    # the pipelined form (detection tail + loss-sum exchange on the side stream, no host sync between steps) must
+    # reproduce the serial step, also when the inputs change from step to step
+    want = (path.loss_out.clone(), path.det_count.clone(), path.dlogits.clone())
+    other = logits + 0.125
+    for lg in (other, other, logits):
+        path.step(gb, gc, gn, lg, regs, overlap_detect=True)
+    path.join()
+    torch.cuda.synchronize()
+    if not (torch.equal(path.loss_out, want[0]) and torch.equal(path.det_count, want[1]) and
+            torch.equal(path.dlogits, want[2])):
+        raise SystemExit('MISMATCH overlapped step vs serial step (%s): %s vs %s' % (
+            mode, path.loss_out.tolist(), want[0].tolist()))
+    path.check_status(ignore=12)
     return path, logits, regs
 
 
