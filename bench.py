@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument('--topk', type=int, default=1000)
     ap.add_argument('--no-overlap', action='store_true', help='keep the detection tail on the main stream')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
+    ap.add_argument('--flip', action='store_true',
+                    help="the reference's [orig, flipped] batches (dataset.py:182-204): --batch counts source images, the "
+                         'step runs on twice as many')
     ap.add_argument('--graph', action='store_true',
                     help='replay the step as one CUDA graph (DenseHeadPath.capture); single GPU, for launch-bound '
                          'small workloads')
@@ -184,6 +187,7 @@ def workload_config(wl, args, batch):
                     'fwd+bwd, decode + score>0.5 + per-class NMS IoU 0.5' % (
                         wl.name, wl.image_h, wl.image_w, wl.num_classes, wl.max_gt, batch, args.cls_mode),
         'images_per_gpu': batch, 'cls_mode': args.cls_mode,
+        'orig_plus_flipped': bool(getattr(args, 'flip', False)),
         'logits': 'N(-4.595, %.2f^2) + N(6,1) on (positive anchor, class)' % args.logit_sigma,
         'l2': 'inputs (%.1f GB logits per step) exceed the 126 MB L2; no flush needed' % (
             batch * 4e-9 * wl.num_classes * anchors_of(wl)),
@@ -340,14 +344,17 @@ def run_b200(args):
         sampler.start()
 
     # ---- inputs resident in HBM
+    src_batch = batch
+    if args.flip:
+        batch = 2 * src_batch     # images per step: [orig, flipped]
     path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, cls_mode=args.cls_mode,
                          capacity=8192, process_group=None if world > 1 else False, device=dev,
                          exchange=args.exchange)
-    gt_boxes_h, gt_classes_h, gt_counts_h = synthetic.gt_batch(wl, batch, first_image=rank * batch)
+    gt_boxes_h, gt_classes_h, gt_counts_h = synthetic.gt_batch(wl, src_batch, first_image=rank * src_batch)
     gt_boxes = torch.from_numpy(gt_boxes_h).to(dev)
     gt_classes = torch.from_numpy(gt_classes_h).to(dev)
     gt_counts = torch.from_numpy(gt_counts_h).to(dev)
-    path.assign(gt_boxes, gt_classes, gt_counts)
+    path.assign(gt_boxes, gt_classes, gt_counts, with_flip=args.flip)
     logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=1000 + rank, device=dev,
                                            logit_sigma=args.logit_sigma)
     if args.logits_dtype == 'bf16':
@@ -406,14 +413,14 @@ def run_b200(args):
     if args.graph:
         if world > 1:
             raise SystemExit('--graph is single-GPU')
-        graph = path.capture(gt_boxes, gt_classes, gt_counts, logits, regs)
+        graph = path.capture(gt_boxes, gt_classes, gt_counts, logits, regs, with_flip=args.flip)
         overlap = False
 
     def one_step():
         if graph is not None:
             graph.replay()
         else:
-            path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap)
+            path.step(gt_boxes, gt_classes, gt_counts, logits, regs, overlap_detect=overlap, with_flip=args.flip)
 
     # extra untimed warm-up until the clock sampler delivers (rank 0 decides, every rank runs the same steps)
     warmup_extra = 0
@@ -446,7 +453,7 @@ def run_b200(args):
         # and time them on a few eager steps after the timed region
         l0 = _lib.lib.rn_launch_count()
         for _ in range(10):
-            path.step(gt_boxes, gt_classes, gt_counts, logits, regs)
+            path.step(gt_boxes, gt_classes, gt_counts, logits, regs, with_flip=args.flip)
         torch.cuda.synchronize()
         launches = (_lib.lib.rn_launch_count() - l0) // 10 * args.steps
     record['on'] = False
@@ -486,7 +493,7 @@ def run_b200(args):
         b_, c_, n_ = (x.to(dev, non_blocking=True) for x in h_gt)
         d_logits.copy_(h_logits, non_blocking=True)
         d_regs.copy_(h_regs, non_blocking=True)
-        path.step(b_, c_, n_, d_logits, d_regs)
+        path.step(b_, c_, n_, d_logits, d_regs, with_flip=args.flip)
         h_out['loss'].copy_(path.loss_out, non_blocking=True)
         h_out['det_boxes'].copy_(path.det_boxes, non_blocking=True)
         h_out['det_scores'].copy_(path.det_scores, non_blocking=True)

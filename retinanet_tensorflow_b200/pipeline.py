@@ -376,7 +376,8 @@ class DenseHeadPath(object):
         return self.det_boxes, self.det_scores, self.det_classes, self.det_count
 
     # ---- one whole step of the hot path -----------------------------------------------------
-    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True, overlap_detect=False):
+    def step(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True, overlap_detect=False,
+             with_flip=False):
         """assign -> loss fwd+bwd -> decode/select/NMS.  With `fused` (default) and a supported
         configuration the loss kernel also does the candidate selection (logits read once).
 
@@ -385,8 +386,11 @@ class DenseHeadPath(object):
         events keep the select workspace from being overwritten early.  The loss-sum exchange and
         the final normalisation (`loss_out`) ride on the side stream too (unless the exchange is an
         NCCL collective).  Detections and `loss_out` are then valid after `join()` (or a device
-        synchronize); gradients are on the current stream as always."""
-        self.assign(gt_boxes, gt_classes, gt_counts)
+        synchronize); gradients are on the current stream as always.
+
+        with_flip=True: the ground truth holds batch/2 images and the batch is the reference's
+        `[orig, flipped]` sample (see `assign`)."""
+        self.assign(gt_boxes, gt_classes, gt_counts, with_flip=with_flip)
         if not (fused and self.fused_select_supported()):
             self.join()
             self.loss(logits, regression)
@@ -418,7 +422,7 @@ class DenseHeadPath(object):
             self._side_done.record(self._side)
         return self.loss_out, self.det_count
 
-    def capture(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True, warmup=2):
+    def capture(self, gt_boxes, gt_classes, gt_counts, logits, regression, fused=True, warmup=2, with_flip=False):
         """Record one whole `step()` on these (static) buffers into a CUDA graph and return it;
         `graph.replay()` then re-runs the step with one launch -- for small workloads (Shapes, VOC, small
         batches) the ~10 kernel launches of a step cost more than the kernels.  Refill the same input
@@ -434,11 +438,11 @@ class DenseHeadPath(object):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):     # warm-up outside the capture: allocates dlogits / dreg
                 for _ in range(max(1, warmup)):
-                    self.step(gt_boxes, gt_classes, gt_counts, logits, regression, fused=fused)
+                    self.step(gt_boxes, gt_classes, gt_counts, logits, regression, fused=fused, with_flip=with_flip)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self.step(gt_boxes, gt_classes, gt_counts, logits, regression, fused=fused)
+                self.step(gt_boxes, gt_classes, gt_counts, logits, regression, fused=fused, with_flip=with_flip)
         finally:
             self.stage_hook = hook
         return graph
