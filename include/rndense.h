@@ -62,7 +62,7 @@ typedef enum rn_status {
 #define RN_FLAG_IOU_RANGE 2u      /* IoU NaN or outside [0,1]  (utils.py:94)                  */
 #define RN_FLAG_CAND_OVERFLOW 4u  /* more candidates than `capacity`; extra ones dropped      */
 #define RN_FLAG_DET_OVERFLOW 8u   /* more detections than `out_capacity`; extra ones dropped  */
-#define RN_FLAG_EXCHANGE_TIMEOUT 32u /* a peer's message did not arrive within ~2 s (rn_stats_exchange) */
+#define RN_FLAG_EXCHANGE_TIMEOUT 32u /* a peer's message did not arrive in time (rn_stats_exchange): fatal, NaN */
 #define RN_FLAG_EMPTY_GT 16u      /* an image had 0 GT boxes (reference asserts >= 1,
                                      data_loaders/inferred.py:30); handled as all-background  */
 
@@ -236,6 +236,24 @@ RN_API int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const 
                             const rn_maps_t* label, const rn_maps_t* fg_mask, const rn_maps_t* dpred,
                             double* d_stats, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The loss stage of a training step in ONE launch (train.py:218-220): classification loss forward + backward
+ * (as rn_cls_loss_fwd_bwd, compact labels), Huber regression loss forward + backward (as rn_huber_fwd_bwd,
+ * fg = label >= 0), and -- capacity > 0 -- the candidate pre-selection of rn_cls_loss_select
+ * (utils.boxes_decode, utils.py:183-190; finish with rn_select_finalize).  d_loss_out (optional, float[4]): the
+ * final scalars of rn_loss_finalize, written by the same launch -- single GPU only, where no statistics exchange
+ * has to happen between the sums and the normalisation.  d_stats_next (optional): another statistics vector
+ * (RN_STATS_HEADER + 3 * num_classes doubles) that the same launch leaves zeroed for the next step's
+ * rn_assign_encode, so a training loop that rotates its statistics vectors needs no memset.  The first 256 bytes of d_loss_workspace must be zero
+ * before the first use; every kernel leaves them zero.  Shapes the streaming kernel does not take (C % 4 != 0,
+ * focus != 2) run as separate launches; the fused selection is then RN_ERR_UNSUPPORTED
+ * (rn_fused_select_supported). */
+RN_API int rn_head_loss(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits, const rn_maps_t* label,
+                        int mode, float focus, float alpha, float eps, const rn_maps_t* dlogits, int logits_dtype,
+                        const rn_maps_t* reg_pred, const rn_maps_t* reg_target, const rn_maps_t* dreg,
+                        double* d_stats, double* d_stats_next, void* d_loss_workspace, size_t loss_workspace_bytes,
+                        float* d_loss_out, float score_thr, int capacity, int32_t* d_cand_count, uint32_t* d_status,
+                        void* d_select_workspace, size_t select_workspace_bytes, void* stream);
+
 /* The same loss for the reference's own call shape: [rows, width] arrays of any width and a
  * u8 fg mask [rows] (losses_test.py:17-27 uses width 1).  Reads num_fg from d_stats, writes
  * the scalar loss to d_loss and (optional) the gradient to d_dpred. */
@@ -268,6 +286,18 @@ RN_API int rn_colsum_backward(int64_t rows, int num_classes, const float* d_labe
                               const float* d_logits, const float* d_a, const float* d_b,
                               float* d_grad, void* stream);
 
+/* ---- trainable masking ------------------------------------------------------------------- */
+/* tf.boolean_mask(x, trainable_mask) per level + concat over levels (utils.postprocess_and_mask,
+ * utils.py:258-284; utils.merge_outputs, utils.py:151-153): order-preserving compaction of the rows whose
+ * u8 mask is non-zero, (level, b, y, x, a) order.  rn_mask_scan counts and scans once per mask (d_count:
+ * device int64, M); rn_mask_gather copies one tensor ([rows, row_bytes] per level -> d_out [M, row_bytes]) and
+ * can be repeated for every tensor that shares the mask (labels, logits, probabilities, regressions). */
+RN_API size_t rn_mask_workspace_bytes(const rn_rows_t* rows);
+RN_API int rn_mask_scan(const rn_rows_t* rows, const rn_maps_t* mask, void* d_workspace, size_t workspace_bytes,
+                        int64_t* d_count, void* stream);
+RN_API int rn_mask_gather(const rn_rows_t* rows, int row_bytes, const rn_maps_t* src, const rn_maps_t* mask,
+                          const void* d_workspace, void* d_out, void* stream);
+
 /* ---- multi-GPU exchange over NVLink peer memory -------------------------------------------- */
 /* All-reduce(sum) of d_stats[offset : offset + len) across `world` ranks WITHOUT a collective
  * library: every rank owns a mailbox of rn_stats_mailbox_bytes() in peer-mapped memory (zeroed
@@ -276,11 +306,17 @@ RN_API int rn_colsum_backward(int64_t rows, int num_classes, const float* d_labe
  * kernel stores the slice into every peer, publishes `epoch` (must increase by 1 per use of a
  * phase; use slot = 2 * phase + (epoch & 1) so that a slot is never rewritten before it is read),
  * waits for all ranks' messages and sums them in rank order: results are bit-identical on all
- * ranks.  A peer that never arrives sets RN_FLAG_EXCHANGE_TIMEOUT after ~2 s instead of hanging. */
+ * ranks.  A peer that does not arrive within the limit (default 10 min, rn_set_option("exchange_timeout_ms", ms))
+ * is FATAL: the slice becomes NaN and RN_FLAG_EXCHANGE_TIMEOUT is raised -- never local-only statistics.
+ * rn_stats_exchange_auto keeps the epochs in device memory (d_epochs: `phases` uint64 counters, zeroed once,
+ * incremented by the kernel; mailbox sized for slots = 2 * phases), which makes the call graph-capturable. */
 RN_API size_t rn_stats_mailbox_bytes(int world, int len_max, int slots);
 RN_API int rn_stats_exchange(double* d_stats, int offset, int len, int len_max, int world, int rank,
                              const void* const* d_peer_mailboxes, int slot, int slots, uint64_t epoch,
                              uint32_t* d_status, void* stream);
+RN_API int rn_stats_exchange_auto(double* d_stats, int offset, int len, int len_max, int world, int rank,
+                                  const void* const* d_peer_mailboxes, int phase, int phases, uint64_t* d_epochs,
+                                  uint32_t* d_status, void* stream);
 
 /* ---- decode + select + NMS ------------------------------------------------------------ */
 /* tf.nn.sigmoid (utils.py:249) with the same device function the fused kernels use. */

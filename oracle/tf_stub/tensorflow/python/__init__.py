@@ -1,0 +1,1 @@
+"""NumPy stand-in (see ../__init__.py)."""

@@ -60,7 +60,8 @@ class Maps(C.Structure):
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'librndense.so')
+# RNDENSE_LIB points at another build of the same library (tuning variants); default: the in-tree build
+LIB_PATH = os.environ.get('RNDENSE_LIB') or os.path.join(_HERE, 'lib', 'librndense.so')
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -95,14 +96,20 @@ PROTOTYPES = {
     'rn_cls_sums': (_i, [_RP, _i, _MP, _MP, _i, _i, _vp, _vp, _sz, _vp]),
     'rn_cls_loss_fwd_bwd': (_i, [_RP, _i, _MP, _MP, _i, _i, _f, _f, _f, _MP, _i, _vp, _vp, _sz, _vp]),
     'rn_huber_fwd_bwd': (_i, [_RP, _MP, _MP, _MP, _MP, _MP, _vp, _vp, _sz, _vp]),
+    'rn_head_loss': (_i, [_RP, _i, _MP, _MP, _i, _f, _f, _f, _MP, _i, _MP, _MP, _MP, _vp, _vp, _vp, _sz, _vp, _f, _i, _vp, _vp,
+                     _vp, _sz, _vp]),
     'rn_huber_rows': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_loss_finalize': (_i, [_i, _i, _vp, _vp, _vp]),
     'rn_cls_loss_elementwise': (_i, [_i64, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     'rn_focal_softmax': (_i, [_i64, _i, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
     'rn_colsum_backward': (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     'rn_sigmoid': (_i, [_i64, _vp, _vp, _vp]),
+    'rn_mask_workspace_bytes': (_sz, [_RP]),
+    'rn_mask_scan': (_i, [_RP, _MP, _vp, _sz, _vp, _vp]),
+    'rn_mask_gather': (_i, [_RP, _i, _MP, _MP, _vp, _vp, _vp]),
     'rn_stats_mailbox_bytes': (_sz, [_i, _i, _i]),
     'rn_stats_exchange': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, C.c_uint64, _vp, _vp]),
+    'rn_stats_exchange_auto': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     'rn_decode_boxes': (_i, [_PP, _i, _MP, _MP, _vp]),
     'rn_boxmap_op': (_i, [_PP, _i, _i, _MP, _MP, _vp]),
     'rn_classmap_fg': (_i, [_i64, _i, _vp, _f, _vp, _vp]),

@@ -29,7 +29,11 @@ struct AssignParams {
   int tpc;  // threads per cell
 };
 
-__global__ void __launch_bounds__(kTileH * kTileW * 6)
+#ifndef RN_ASSIGN_MAXNREG
+#define RN_ASSIGN_MAXNREG 48
+#endif
+__global__ void __maxnreg__(RN_ASSIGN_MAXNREG)   // two CTAs must fit beside the resident loss kernel (prefetch_assign), see DESIGN.md
+
 assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ AssignParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_box = reinterpret_cast<float4*>(smem_raw);                       // [max_gt] recomputed corners
@@ -158,7 +162,9 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
         const float inter = fmul(fsub(yb, yt), fsub(xr, xl));
         const float uni = fsub(fadd(aa[k], ga), inter);
         const float approx = inter * rcp_approx(uni);
-        if (approx * 1.000002f > best[k]) {
+        // (best == 0: always take the exact division -- a denormal intersection flushes `approx` to 0, but the
+        //  reference's argmax still prefers that tiny positive IoU over "no overlap")
+        if (approx * 1.000002f > best[k] || best[k] == 0.f) {
           const float v = fdiv(inter, uni);
           if (v > best[k]) {
             best[k] = v;
@@ -193,9 +199,12 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
       } else if (ign) {
         lab = RN_LABEL_IGNORE;
       }
+      // deltas are compared within 1e-5 relative, not bit-exactly.  The shifts take a reciprocal (rcp.approx + one
+      // Newton step, <= 1 ulp of the quotient); the scale ratios keep the IEEE division, because log() of a ratio
+      // near 1 turns a 2-ulp ratio error into an arbitrarily large RELATIVE error of a near-zero delta.
       const float h = L.anchor_h[a], w = L.anchor_w[a];
-      d.x = fdiv(fsub(t.x, cy), h);   // shifts, dataset.py:108
-      d.y = fdiv(fsub(t.y, cx), w);
+      d.x = fsub(t.x, cy) * rcp_newton(h);   // shifts, dataset.py:108
+      d.y = fsub(t.y, cx) * rcp_newton(w);
       const float rh = fdiv(t.z, h), rw = fdiv(t.w, w);   // scales, dataset.py:110
       d.z = log_fast(rh);                                 // log(scales), dataset.py:112
       d.w = log_fast(rw);
@@ -388,6 +397,22 @@ extern "C" int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float*
   const size_t smem = (size_t)max_gt * (2 * sizeof(float4) + sizeof(float) + 2 * sizeof(int));
   const long long blocks = (long long)batch * pyr->tiles_per_image;
   RN_REQUIRE(blocks < (1ll << 31), RN_ERR_BAD_SHAPE, "too many tiles");
+  static size_t smem_opted = 48 * 1024;   // more than 48 KB of dynamic shared memory needs an opt-in (max_gt > ~1100)
+  if (smem > smem_opted) {
+    if (cudaFuncSetAttribute(assign_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      rn::set_error("rn_assign_encode: %zu bytes of shared memory for max_gt = %d refused", smem, max_gt);
+      return RN_ERR_UNSUPPORTED;
+    }
+    smem_opted = smem;
+  }
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // Same shared-memory carve-out as the streaming loss kernel (which needs the maximum): two kernels only share an
+    // SM when they agree on the L1 / shared split, and prefetch_assign runs this kernel beside that one.
+    cudaFuncSetAttribute(assign_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
   assign_encode_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(*pyr, prm);
   RN_CUDA_CHECK_LAUNCH("rn_assign_encode");
   return RN_OK;

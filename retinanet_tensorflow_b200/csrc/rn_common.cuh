@@ -20,6 +20,7 @@ namespace rn {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int num_sms();
+void set_exchange_timeout_ms(long long ms);
 
 #define RN_REQUIRE(cond, status, ...)  \
   do {                                 \

@@ -842,7 +842,11 @@ extern "C" int rn_select_finalize(const rn_pyramid_t* pyr, int batch, const rn_m
   fp.out_anchor = d_cand_anchor;
   fp.count = d_cand_count;
   const size_t smem = sort_smem_bytes(capacity);
-  cudaFuncSetAttribute(cand_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
+  static bool finalize_opted = false;   // once per process, not per call
+  if (!finalize_opted) {
+    cudaFuncSetAttribute(cand_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
+    finalize_opted = true;
+  }
   cand_finalize_kernel<<<batch, kSortThreads, smem, st>>>(*pyr, batch, fp);
   RN_CUDA_CHECK_LAUNCH("rn_select_finalize");
   return RN_OK;
@@ -912,8 +916,12 @@ extern "C" int rn_nms_classwise(int batch, int num_classes, int capacity, const 
   RN_REQUIRE(greedy_smem <= 200 * 1024, RN_ERR_UNSUPPORTED,
              "rn_nms_classwise: max_output_per_class too large for shared memory (limit %d)",
              (int)(200 * 1024 / (kNmsWarps * sizeof(NmsBox))));
-  cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
-  cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static bool nms_opted = false;   // once per process, not per call
+  if (!nms_opted) {
+    cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemElems * 12);
+    cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    nms_opted = true;
+  }
   nms_sort_kernel<<<batch, kSortThreads, sort_smem_bytes(capacity), st>>>(p);
   RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(sort)");
   const long long pairs = (long long)batch * num_classes;

@@ -1262,6 +1262,10 @@ extern "C" int rn_set_option(const char* name, int value) {
     g_fast_kernels = value != 0;
     return RN_OK;
   }
+  if (strcmp(name, "exchange_timeout_ms") == 0) {
+    rn::set_exchange_timeout_ms(value);
+    return RN_OK;
+  }
   if (strcmp(name, "tile_kernel") == 0) {
     g_tile_kernel = value != 0;
     return RN_OK;
@@ -1430,6 +1434,25 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
   const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_kernels && fits32 &&
                        num_classes <= 2048;
+  if (dense && !bf16 && vec4 && g_fast_kernels && g_tile_kernel && (base != RN_CLS_FOCAL || focus == 2.0f) &&
+      cls_tile_supported(num_classes, false, true)) {
+    // dense float labels [rows, C] (the reference's own loss signatures, losses.py:115-141): the streaming
+    // kernel with a second tile of labels per stage
+    TileParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.logits = prm.logits;
+    tp.label = prm.label;
+    tp.dlogits = prm.dlogits;
+    tp.alpha = alpha;
+    tp.eps = eps;
+    tp.stats = d_stats;
+    tp.stats_out = d_stats;
+    tp.workspace = d_workspace;
+    tp.num_classes = num_classes;
+    tp.dense = 1;
+    tp.write_grad = prm.write_grad;
+    return launch_cls_tile(segs, tp, mode, false, st);
+  }
   RN_REQUIRE(!bf16 || (fast_ok && (dice || base != RN_CLS_NONE) && num_classes % 8 == 0), RN_ERR_UNSUPPORTED,
              "bfloat16 logits need the fast kernel: compact labels, C %% 8 == 0, focal (focus 2) / BCE / balanced BCE "
              "and/or dice");
@@ -1546,6 +1569,97 @@ extern "C" int rn_cls_loss_select(const rn_rows_t* rows, int num_classes, const 
   cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * rows->images, st);
   const long long units = segs.start[RN_MAX_LEVELS] * (long long)fp.cv;
   return launch_fast(segs, fp, mode, true, units, st);
+}
+
+// One launch for the whole loss stage of a training step: classification loss forward + backward, Huber
+// regression loss forward + backward, optional candidate pre-selection (capacity > 0) and -- when d_loss_out is
+// given (single GPU: no statistics exchange in between) -- the final scalars.
+extern "C" int rn_head_loss(const rn_rows_t* rows, int num_classes, const rn_maps_t* logits, const rn_maps_t* label,
+                            int mode, float focus, float alpha, float eps, const rn_maps_t* dlogits, int logits_dtype,
+                            const rn_maps_t* reg_pred, const rn_maps_t* reg_target, const rn_maps_t* dreg,
+                            double* d_stats, double* d_stats_next, void* d_loss_workspace, size_t loss_workspace_bytes,
+                            float* d_loss_out, float score_thr, int capacity, int32_t* d_cand_count, uint32_t* d_status,
+                            void* d_select_workspace, size_t select_workspace_bytes, void* stream) {
+  int rc = check_rows(rows, "rn_head_loss");
+  if (rc) return rc;
+  RN_REQUIRE(maps_present(logits) && maps_present(label) && maps_present(reg_pred) && maps_present(reg_target) &&
+                 d_stats && d_loss_workspace,
+             RN_ERR_BAD_ARG, "rn_head_loss: NULL input");
+  RN_REQUIRE(num_classes >= 1, RN_ERR_BAD_ARG, "rn_head_loss: num_classes must be >= 1");
+  RN_REQUIRE(loss_workspace_bytes >= rn_loss_workspace_bytes(num_classes), RN_ERR_CAPACITY,
+             "rn_head_loss: loss workspace too small");
+  const int base = mode & 15;
+  const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
+  RN_REQUIRE(base >= RN_CLS_NONE && base <= RN_CLS_BALANCED_BCE && (mode & ~(15 | RN_CLS_DICE_FLAG)) == 0 &&
+                 (base != RN_CLS_NONE || dice),
+             RN_ERR_BAD_ARG, "rn_head_loss: unknown mode %d", mode);
+  RN_REQUIRE(logits_dtype == RN_DTYPE_F32 || logits_dtype == RN_DTYPE_BF16, RN_ERR_BAD_ARG, "unknown logits_dtype");
+  const bool bf16 = logits_dtype == RN_DTYPE_BF16;
+  const bool select = capacity > 0;
+  const bool grad = maps_present(dlogits);
+  const bool aligned = aligned16(logits, rows->num_segments) && (!grad || aligned16(dlogits, rows->num_segments)) &&
+                       aligned16(reg_pred, rows->num_segments) && aligned16(reg_target, rows->num_segments) &&
+                       (!maps_present(dreg) || aligned16(dreg, rows->num_segments));
+  const bool tile_ok = g_fast_kernels && g_tile_kernel && aligned && (base != RN_CLS_FOCAL || focus == 2.0f) &&
+                       cls_tile_supported(num_classes, bf16, false);
+  if (!tile_ok) {   // separate launches (generic kernels); the fused selection needs the tile kernel
+    RN_REQUIRE(!select, RN_ERR_UNSUPPORTED,
+               "rn_head_loss: the fused candidate selection needs focus == 2 (focal), C %% 4 == 0 and 16-byte aligned "
+               "maps; use rn_decode_select");
+    rc = rn_cls_loss_fwd_bwd(rows, num_classes, logits, label, 0, mode, focus, alpha, eps, dlogits, logits_dtype, d_stats,
+                             d_loss_workspace, loss_workspace_bytes, stream);
+    if (rc) return rc;
+    rc = rn_huber_fwd_bwd(rows, reg_pred, reg_target, label, nullptr, dreg, d_stats, d_loss_workspace,
+                          loss_workspace_bytes, stream);
+    if (rc) return rc;
+    if (d_stats_next)
+      cudaMemsetAsync(d_stats_next, 0, sizeof(double) * (RN_STATS_HEADER + 3 * (size_t)num_classes), (cudaStream_t)stream);
+    return d_loss_out ? rn_loss_finalize(num_classes, mode, d_stats, d_loss_out, stream) : RN_OK;
+  }
+  const Segs segs = make_segs(rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  TileParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.logits = make_ptrs(logits);
+  tp.label = make_ptrs(label);
+  tp.dlogits = make_ptrs(grad ? dlogits : nullptr);
+  tp.pred = make_ptrs(reg_pred);
+  tp.target = make_ptrs(reg_target);
+  tp.dpred = make_ptrs(maps_present(dreg) ? dreg : nullptr);
+  tp.alpha = alpha;
+  tp.eps = eps;
+  tp.stats = d_stats;
+  tp.stats_out = d_stats;
+  tp.workspace = d_loss_workspace;   // counters are left at zero by every kernel that uses them
+  tp.num_classes = num_classes;
+  tp.bf16 = bf16 ? 1 : 0;
+  tp.write_grad = grad ? 1 : 0;
+  tp.loss_out = d_loss_out;
+  tp.final_mode = mode;
+  tp.stats_next = d_stats_next;
+  if (select) {
+    RN_REQUIRE(d_select_workspace && d_cand_count && rows->images >= 1, RN_ERR_BAD_ARG, "rn_head_loss: NULL select output");
+    RN_REQUIRE(score_thr > 0.f && score_thr < 1.f, RN_ERR_BAD_ARG, "rn_head_loss: score_thr must be in (0, 1)");
+    RN_REQUIRE(select_workspace_bytes >= rn_select_workspace_bytes(rows->images, capacity), RN_ERR_CAPACITY,
+               "rn_head_loss: select workspace too small");
+    for (int i = 0; i < rows->num_segments; ++i)
+      RN_REQUIRE(rows->rows[i] % rows->images == 0, RN_ERR_BAD_SHAPE, "rows[%d] is not a multiple of images", i);
+    const double lg = std::log((double)score_thr / (1.0 - (double)score_thr));
+    tp.sel_trigger = (float)(lg - 1e-3 * (1.0 + std::fabs(lg)));
+    tp.sel_thr = score_thr;
+    tp.sel_images = rows->images;
+    tp.sel_capacity = capacity;
+    const size_t n = (size_t)rows->images * capacity;
+    const size_t chunk = (n * 4 + 255) & ~(size_t)255;  // same carving as rn_decode_select
+    char* ws = (char*)d_select_workspace;
+    tp.sel_anchor = (int32_t*)ws;
+    tp.sel_score = (float*)(ws + chunk);
+    tp.sel_class = (int32_t*)(ws + 2 * chunk);
+    tp.sel_count = d_cand_count;
+    tp.status = d_status;
+    cudaMemsetAsync(d_cand_count, 0, sizeof(int32_t) * rows->images, st);
+  }
+  return launch_cls_tile(segs, tp, mode, select, st);
 }
 
 extern "C" int rn_huber_fwd_bwd(const rn_rows_t* rows, const rn_maps_t* pred, const rn_maps_t* target,

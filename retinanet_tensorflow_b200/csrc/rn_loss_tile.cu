@@ -27,12 +27,26 @@
 
 namespace rn {
 
-constexpr int kConsumerWarps = 10;
+// Tuning constants (overridable with -D for the sweeps recorded in profiles/r02_tile_sweep.md)
+#ifndef RN_TILE_CWARPS
+#define RN_TILE_CWARPS 8
+#endif
+#ifndef RN_TILE_STAGES
+#define RN_TILE_STAGES 4
+#endif
+#ifndef RN_TILE_BYTES
+#define RN_TILE_BYTES 20480
+#endif
+#ifndef RN_TILE_MINB
+#define RN_TILE_MINB 2
+#endif
+constexpr int kConsumerWarps = RN_TILE_CWARPS;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTileThreads = kConsumerThreads + 32;   // + one producer warp
-constexpr int kStages = 4;
+constexpr int kStages = RN_TILE_STAGES;      // ring depth (compact labels); dense labels: half, stages are twice as big
+constexpr int kMaxStages = 8;
 constexpr int kQueueCap = 64;        // per-warp queue entries (<= 31 left over + <= 32 pushed)
-constexpr int kTileBytes = 20480;    // target bytes of logits per tile
+constexpr int kTileBytes = RN_TILE_BYTES;    // target bytes of logits per tile
 constexpr int kMaxTileRows = 2048;
 constexpr int kUnitsPerThread = (kTileBytes / 16 + kConsumerThreads - 1) / kConsumerThreads;   // units of a tile per thread
 constexpr float kFix = 68719476736.0f;   // fixed-point scale of the loss accumulators (2^36)
@@ -44,16 +58,19 @@ struct TileDev {
   const double* stats;
   double* stats_out;
   unsigned* counters;          // [0] finish ticket, [2] tile ticket
-  long long* partials;         // [grid][4]
+  long long* partials;         // [grid][8]: high / low words of the three fixed-point sums
   int num_classes;
   unsigned cv;                 // 16-byte units per row
-  unsigned div_magic;          // ceil(2^32 / cv)
   unsigned tile_rows;
   unsigned total_tiles;
   unsigned tile_start[RN_MAX_LEVELS + 1];
   unsigned stage_bytes, x_bytes;   // x_bytes: offset of the label area inside a stage
+  unsigned stages;                 // ring depth
   unsigned tab_bytes;
   int write_grad, huber;
+  float* loss_out;
+  int final_mode;
+  double* stats_next;
   float plain_bound;           // a unit is "plain" when its max logit is <= this (min(-0.70, select trigger))
   float sel_trigger, sel_thr;
   int sel_images, sel_capacity;
@@ -113,6 +130,17 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 // Two confident negatives (logit <= -0.70, z = 0) of the focal loss: the packed twin of focal_neg_bulk
 // (rn_loss_math.cuh), same operations in the same order.  Returns w^2 log(q + eps); grad is scaled by cg.
 __device__ __forceinline__ float2 focal_neg_bulk2(float2 x, float2 eps, float2 cg, float2& grad, float2& pq) {
+#ifdef RN_TILE_MUFU2
+  // two MUFU per logit: E = e^x, r = 1/(1+E); p = E r, and 1/(q + eps) = d (1 - eps d) with d = 1 + E = 1/q
+  const float2 t = mul2(x, f2(1.44269502163e+00f));
+  float2 e, p, r;
+  e.x = ex2_approx(t.x);
+  e.y = ex2_approx(t.y);
+  const float2 d = add2(e, f2(1.0f));
+  r.x = rcp_approx(d.x);
+  r.y = rcp_approx(d.y);
+  p = mul2(e, r);
+#else
   const float2 t = mul2(x, f2(-1.44269502163e+00f));
   float2 e, p, r;
   e.x = ex2_approx(t.x);
@@ -120,6 +148,7 @@ __device__ __forceinline__ float2 focal_neg_bulk2(float2 x, float2 eps, float2 c
   const float2 d = add2(e, f2(1.0f));
   p.x = rcp_approx(d.x);
   p.y = rcp_approx(d.y);
+#endif
   const float2 q = fma2(p, f2(-1.0f), f2(1.0f));    // prob_true = 1 - p
   const float2 w = fma2(q, f2(-1.0f), f2(1.0f));    // the reference's naive 1 - prob_true
   const float2 pe = add2(q, eps);
@@ -132,8 +161,12 @@ __device__ __forceinline__ float2 focal_neg_bulk2(float2 x, float2 eps, float2 c
   s = fma2(s, f, f2(-4.999949932e-01f));
   const float2 lg = fma2(mul2(f, f), s, f);
   const float2 u = mul2(w, lg);
+#ifdef RN_TILE_MUFU2
+  r = fma2(mul2(d, d), mul2(eps, f2(-1.0f)), d);
+#else
   r.x = rcp_approx(pe.x);
   r.y = rcp_approx(pe.y);
+#endif
   const float2 v = fma2(f2(-2.0f), u, mul2(mul2(w, w), r));
   pq = mul2(p, q);
   grad = mul2(mul2(cg, v), pq);
@@ -328,7 +361,7 @@ struct __align__(16) QEntry {
 // MODE: RN_CLS_FOCAL (focus 2) | RN_CLS_BCE | RN_CLS_BALANCED_BCE | RN_CLS_NONE; DICE adds the dice gradient.
 // SELECT: fused candidate pre-selection.  BF16: bf16x8 units.  DENSE: float labels [rows, C], all rows trainable.
 template <int MODE, bool DICE, bool SELECT, bool BF16, bool DENSE>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, RN_TILE_MINB)
 cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileDev prm) {
   extern __shared__ __align__(128) unsigned char smem[];
   // [0,64) full barriers, [64,128) empty barriers, [128,256) tile info, then tables, queues, stages
@@ -338,7 +371,7 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
   constexpr unsigned kEntry = DENSE ? 48u : 32u;
   unsigned char* s_queue = smem + 256 + prm.tab_bytes;
   unsigned char* s_stage = s_queue + kConsumerWarps * kQueueCap * kEntry;
-  __shared__ long long s_red[3][kConsumerWarps];
+  __shared__ long long s_red[6][kConsumerWarps];
   __shared__ bool s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -349,7 +382,7 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
   const double M = prm.stats[RN_STAT_TRAINABLE];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(bar_full + 8 * i, 1 + (DENSE ? 0 : 32));   // expect_tx arrive (+ one per producer lane: labels)
       mbar_init(bar_empty + 8 * i, kConsumerWarps);
     }
@@ -378,18 +411,23 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
   __syncthreads();
 
   const unsigned cv = prm.cv;
+  const unsigned nstages = prm.stages;
   long long fx_neg = 0, fx_pos = 0, fx_hub = 0;
 
   if (warp == kConsumerWarps) {
     // ================= producer warp: tickets + bulk copies =================
     const unsigned row_bytes = cv * 16u;
-    for (unsigned it = 0;; ++it) {
-      const unsigned stage = it % kStages;
-      if (it >= kStages) mbar_wait(bar_empty + 8 * stage, ((it / kStages) - 1) & 1);
+    unsigned stage = 0, round = 0;   // ring position without a runtime division per tile
+    for (unsigned it = 0;; ++it, ++stage) {
+      if (stage == nstages) {
+        stage = 0;
+        ++round;
+      }
+      if (round) mbar_wait(bar_empty + 8 * stage, (round - 1) & 1);
       unsigned t = 0;
       if (lane == 0) {
-        // the first kStages tiles of a CTA are static (no ticket latency while the ring fills)
-        t = it < kStages ? it * gridDim.x + blockIdx.x : kStages * gridDim.x + atomicAdd(prm.counters + 2, 1u);
+        // the first `nstages` tiles of a CTA are static (no ticket latency while the ring fills)
+        t = it < nstages ? it * gridDim.x + blockIdx.x : nstages * gridDim.x + atomicAdd(prm.counters + 2, 1u);
       }
       t = __shfl_sync(0xffffffffu, t, 0);
       const uint32_t full = bar_full + 8 * stage;
@@ -500,14 +538,18 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
 #pragma unroll
     for (int k = 0; k < kUnitsPerThread; ++k) {
       const unsigned i = threadIdx.x + (unsigned)k * kConsumerThreads;
-      const unsigned r = __umulhi(i, prm.div_magic);
+      const unsigned r = i / cv;   // once per kernel
       geo[k] = r | (((i - r * cv) * kPerUnit) << 16);
       asm volatile("" : "+r"(geo[k]));   // keep it in a register (the compiler would recompute it per tile)
     }
 
-    for (unsigned it = 0;; ++it) {
-      const unsigned stage = it % kStages;
-      mbar_wait(bar_full + 8 * stage, (it / kStages) & 1);
+    unsigned stage = 0, round = 0;
+    for (;; ++stage) {
+      if (stage == nstages) {
+        stage = 0;
+        ++round;
+      }
+      mbar_wait(bar_full + 8 * stage, round & 1);
       const int4 info = tile_info[stage];
       if (info.x < 0) break;
       const int s = info.x;
@@ -560,8 +602,12 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
           outv = *reinterpret_cast<const Unit*>(&g);
         }
         plain = plain && valid;
-        // the unit's loss only counts when it really was a bulk unit of a trainable row
-        acc = fma2(a2, mul2(live2, f2(plain ? 1.0f : 0.0f)), acc);
+        // the unit's loss only counts when it really was a bulk unit of a trainable row.  A SELECT, not a multiply
+        // by zero: the bulk math of a unit that belongs to the careful path may have overflowed (inf * 0 = NaN)
+        const bool counts = plain && lab != RN_LABEL_IGNORE;
+        a2.x = counts ? a2.x : 0.0f;
+        a2.y = counts ? a2.y : 0.0f;
+        acc = add2(acc, a2);
         if (plain && write_grad) __stcs(gout + i, outv);
         const unsigned m = __ballot_sync(0xffffffffu, valid && !plain);
         if (m) {
@@ -610,62 +656,72 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
     if (qcount) drain(qcount);
   }
 
-  // ---- order-independent reduction: integer sums --------------------------------------------------------
+  // ---- order-independent reduction: integer sums.  A thread's total fits 64 bits with a wide margin; sums ACROSS
+  // threads and CTAs are kept as separate high / low words so that no realistic or adversarial input can overflow.
+  long long acc6[6] = {fx_neg >> 24, fx_neg & 0xffffff, fx_pos >> 24, fx_pos & 0xffffff, fx_hub >> 24, fx_hub & 0xffffff};
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    fx_neg += __shfl_xor_sync(0xffffffffu, fx_neg, o);
-    fx_pos += __shfl_xor_sync(0xffffffffu, fx_pos, o);
-    fx_hub += __shfl_xor_sync(0xffffffffu, fx_hub, o);
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc6[k] += __shfl_xor_sync(0xffffffffu, acc6[k], o);
   }
   if (lane == 0 && warp < kConsumerWarps) {
-    s_red[0][warp] = fx_neg;
-    s_red[1][warp] = fx_pos;
-    s_red[2][warp] = fx_hub;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_red[k][warp] = acc6[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    long long a = 0;
+    for (int w = 0; w < kConsumerWarps; ++w) a += s_red[threadIdx.x][w];
+    prm.partials[8 * (size_t)blockIdx.x + threadIdx.x] = a;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    long long a = 0, b = 0, c = 0;
-    for (int w = 0; w < kConsumerWarps; ++w) {
-      a += s_red[0][w];
-      b += s_red[1][w];
-      c += s_red[2][w];
-    }
-    long long* out = prm.partials + 4 * (size_t)blockIdx.x;
-    out[0] = a;
-    out[1] = b;
-    out[2] = c;
     __threadfence();
     s_last = (atomicAdd(prm.counters, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (s_last && warp == 0) {
     __threadfence();
-    // split every partial into high and low words so the integer sums cannot overflow, then combine in double
-    long long hi[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
+    long long tot[6] = {0, 0, 0, 0, 0, 0};
     for (unsigned i = lane; i < gridDim.x; i += 32) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const long long v = __ldcg(prm.partials + 4 * (size_t)i + k);
-        hi[k] += v >> 24;
-        lo[k] += v & 0xffffff;
-      }
+      for (int k = 0; k < 6; ++k) tot[k] += __ldcg(prm.partials + 8 * (size_t)i + k);
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 6; ++k) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        hi[k] += __shfl_xor_sync(0xffffffffu, hi[k], o);
-        lo[k] += __shfl_xor_sync(0xffffffffu, lo[k], o);
-      }
+      for (int o = 16; o > 0; o >>= 1) tot[k] += __shfl_xor_sync(0xffffffffu, tot[k], o);
     }
+    if (prm.stats_next)   // the next step's statistics vector starts from zero without a launch of its own
+      for (int i = lane; i < RN_STATS_HEADER + 3 * C; i += 32) prm.stats_next[i] = 0.0;
     if (lane == 0) {
       const double sc = 1.0 / 68719476736.0;
-      const double neg = ((double)hi[0] * 16777216.0 + (double)lo[0]) * sc;
-      const double pos = ((double)hi[1] * 16777216.0 + (double)lo[1]) * sc;
-      const double hub = ((double)hi[2] * 16777216.0 + (double)lo[2]) * sc;
+      const double neg = ((double)tot[0] * 16777216.0 + (double)tot[1]) * sc;
+      const double pos = ((double)tot[2] * 16777216.0 + (double)tot[3]) * sc;
+      const double hub = ((double)tot[4] * 16777216.0 + (double)tot[5]) * sc;
       // focal: negatives accumulated w^2 log(q+eps), loss = -(1-alpha) * that; BCE modes: plain sum
       prm.stats_out[RN_STAT_CLS_SUM] = MODE == RN_CLS_FOCAL ? pos - (double)(1.0f - prm.alpha) * neg : pos + neg;
       if (prm.huber) prm.stats_out[RN_STAT_HUBER_SUM] = hub;
+      if (prm.loss_out) {   // single GPU: nothing to exchange, finish the scalars here (as loss_finalize_kernel)
+        const double cls_sum = prm.stats_out[RN_STAT_CLS_SUM];
+        const int base = prm.final_mode & 15;
+        double cls = 0.0;
+        if (base == RN_CLS_FOCAL) cls += cls_sum / fmax(nfg, 1.0);
+        if (base == RN_CLS_BCE || base == RN_CLS_BALANCED_BCE) cls += M > 0 ? cls_sum / (M * (double)C) : 0.0;
+        if (prm.final_mode & RN_CLS_DICE_FLAG) {
+          double dsum = 0.0;
+          for (int c = 0; c < C; ++c) {
+            const double I = prm.stats[RN_STAT_INTER(C, c)];
+            const double U = prm.stats[RN_STAT_NPOS(c)] + prm.stats[RN_STAT_PSUM(C, c)];
+            dsum += 1.0 - 2.0 * I / U;
+          }
+          cls += dsum / (double)C;
+        }
+        prm.loss_out[0] = (float)cls;
+        prm.loss_out[1] = nfg > 0 ? (float)((prm.huber ? hub : prm.stats[RN_STAT_HUBER_SUM]) / (4.0 * nfg)) : 0.0f;
+        prm.loss_out[2] = (float)nfg;
+        prm.loss_out[3] = (float)M;
+      }
       prm.counters[0] = 0;
       prm.counters[2] = 0;
     }
@@ -712,12 +768,18 @@ static int launch_variant(const Segs& segs, const TileDev& dev, size_t smem, cud
 template <int MODE, bool DICE>
 static int launch_mode(const Segs& segs, const TileDev& dev, bool select, bool bf16, bool dense, size_t smem,
                        cudaStream_t st) {
+#ifdef RN_TILE_SWEEP   // tuning builds: only the headline instantiation
+  if (MODE == RN_CLS_FOCAL && !DICE && select && !bf16 && !dense)
+    return launch_variant<RN_CLS_FOCAL, false, true, false, false>(segs, dev, smem, st);
+  return RN_ERR_UNSUPPORTED;
+#else
   if (dense) return launch_variant<MODE, DICE, false, false, true>(segs, dev, smem, st);
   if (bf16)
     return select ? launch_variant<MODE, DICE, true, true, false>(segs, dev, smem, st)
                   : launch_variant<MODE, DICE, false, true, false>(segs, dev, smem, st);
   return select ? launch_variant<MODE, DICE, true, false, false>(segs, dev, smem, st)
                 : launch_variant<MODE, DICE, false, false, false>(segs, dev, smem, st);
+#endif
 }
 
 int launch_cls_tile(const Segs& segs, const TileParams& tp, int mode, bool select, cudaStream_t st) {
@@ -739,10 +801,8 @@ int launch_cls_tile(const Segs& segs, const TileParams& tp, int mode, bool selec
   dev.partials = reinterpret_cast<long long*>(reinterpret_cast<char*>(tp.workspace) + 256);
   dev.num_classes = tp.num_classes;
   dev.cv = (unsigned)(tp.num_classes / (bf16 ? 8 : 4));
-  dev.div_magic = (unsigned)((0x100000000ull + dev.cv - 1) / dev.cv);
   const unsigned row_bytes = dev.cv * 16u;
-  unsigned budget = (unsigned)kTileBytes / (dense ? 2u : 1u);
-  unsigned tr = budget / row_bytes;
+  unsigned tr = (unsigned)kTileBytes / row_bytes;   // dense labels: the stage also holds a label tile of this size
   if (tr < 1) tr = 1;
   if (tr > (unsigned)kMaxTileRows) tr = kMaxTileRows;
   if (tr >= 4) tr &= ~3u;
@@ -766,6 +826,9 @@ int launch_cls_tile(const Segs& segs, const TileParams& tp, int mode, bool selec
   const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
   dev.tab_bytes = (dice || base == RN_CLS_BALANCED_BCE) ? (unsigned)((4 * tp.num_classes * sizeof(float) + 127) & ~127u) : 0u;
   dev.write_grad = tp.write_grad;
+  dev.loss_out = tp.loss_out;
+  dev.final_mode = tp.final_mode;
+  dev.stats_next = tp.stats_next;
   dev.huber = (!dense && tp.pred.p[0] != nullptr) ? 1 : 0;
   dev.sel_trigger = tp.sel_trigger;
   dev.sel_thr = tp.sel_thr;
@@ -777,8 +840,9 @@ int launch_cls_tile(const Segs& segs, const TileParams& tp, int mode, bool selec
   dev.sel_class = tp.sel_class;
   dev.sel_count = tp.sel_count;
   dev.status = tp.status;
+  dev.stages = dense ? (kStages >= 4 ? kStages / 2 : 2) : kStages;
   const size_t smem = 256 + dev.tab_bytes + (size_t)kConsumerWarps * kQueueCap * (dense ? 48 : 32) +
-                      (size_t)kStages * dev.stage_bytes;
+                      (size_t)dev.stages * dev.stage_bytes;
   if (dev.total_tiles == 0) {   // nothing to stream: the sums are zero
     // (kernel launch with grid 1 handles it: the producer immediately publishes the end marker)
   }

@@ -16,6 +16,9 @@ struct TileParams {
   int bf16;                      // logits / dlogits are bfloat16 (bf16x8 units)
   int dense;                     // dense float labels, every row trainable (the reference's own loss signatures)
   int write_grad;
+  float* loss_out;               // optional [4]: final scalars (as rn_loss_finalize) written by the last CTA
+  int final_mode;                //   ... for this RN_CLS_* | RN_CLS_DICE_FLAG mode
+  double* stats_next;            // optional: another statistics vector (RN_STATS_HEADER + 3C), zeroed by the last CTA
   // fused candidate pre-selection (rn_cls_loss_select, utils.boxes_decode, utils.py:183-190)
   float sel_trigger, sel_thr;
   int sel_images, sel_capacity;

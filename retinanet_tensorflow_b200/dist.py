@@ -99,17 +99,14 @@ class PeerExchange(object):
         if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
             raise RuntimeError('symmetric-memory rendezvous returned unexpected peer pointers')
         self.peer_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
-        self.epochs = [0, 0, 0]
+        self.epochs = torch.zeros((len(PHASES),), dtype=torch.int64, device=device)   # advanced by the kernel
         torch.cuda.synchronize(device)
         tdist.barrier(self.group)     # every mailbox is zeroed before anybody posts
         self._C = C
 
     def all_reduce(self, stats, phase, status=None):
-        k = PHASES[phase]
-        self.epochs[k] += 1
-        epoch = self.epochs[k]
         offset, length = phase_slice(phase, self.num_classes)
-        _lib.call('rn_stats_exchange', _lib.ptr(stats), offset, length, self.len_max, self.world, self.rank,
-                  _lib.ptr(self.peer_ptrs), 2 * k + (epoch & 1), self.SLOTS, epoch, _lib.ptr(status),
+        _lib.call('rn_stats_exchange_auto', _lib.ptr(stats), offset, length, self.len_max, self.world, self.rank,
+                  _lib.ptr(self.peer_ptrs), PHASES[phase], len(PHASES), _lib.ptr(self.epochs), _lib.ptr(status),
                   _lib.stream_ptr())
         return stats

@@ -132,21 +132,20 @@ class _ColumnSumLoss(torch.autograd.Function):
     def forward(ctx, labels, logits, formula, axis):
         labels, logits, rows, c = _two_d(labels, logits)
         _, z, i, p = _class_stats(labels, logits)
-        with torch.enable_grad():
-            i_, p_ = i.clone().requires_grad_(True), p.clone().requires_grad_(True)
-            if axis is None:
-                out = formula(z.sum(), i_.sum(), p_.sum())
-            else:
-                out = formula(z, i_, p_)
-        ctx.save_for_backward(labels, logits)
-        ctx.graph = (out, i_, p_)
-        return out.detach().float()
+        out = formula(z.sum(), i.sum(), p.sum()) if axis is None else formula(z, i, p)
+        # only plain tensors are kept: the tiny float64 graph of `formula` is rebuilt in backward, so a second
+        # backward (retain_graph, checkpointing) works and nothing but these tensors outlives the forward
+        ctx.save_for_backward(labels, logits, z, i, p)
+        ctx.formula, ctx.axis = formula, axis
+        return out.float()
 
     @staticmethod
     def backward(ctx, g):
-        labels, logits = ctx.saved_tensors
-        out, i_, p_ = ctx.graph
-        a, b = torch.autograd.grad(out, (i_, p_), g.double().reshape(out.shape), allow_unused=True)
+        labels, logits, z, i, p = ctx.saved_tensors
+        with torch.enable_grad():
+            i_, p_ = i.detach().clone().requires_grad_(True), p.detach().clone().requires_grad_(True)
+            out = ctx.formula(z.sum(), i_.sum(), p_.sum()) if ctx.axis is None else ctx.formula(z, i_, p_)
+            a, b = torch.autograd.grad(out, (i_, p_), g.double().reshape(out.shape), allow_unused=True)
         c = int(logits.shape[-1])
         a = (torch.zeros_like(i_) if a is None else a).float().contiguous()
         b = (torch.zeros_like(p_) if b is None else b).float().contiguous()

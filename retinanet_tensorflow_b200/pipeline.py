@@ -41,7 +41,8 @@ _FLAG_MESSAGES = {
     _lib.RN_FLAG_CAND_OVERFLOW: 'more candidates than `capacity`',
     _lib.RN_FLAG_DET_OVERFLOW: 'more detections than `out_capacity`',
     _lib.RN_FLAG_EMPTY_GT: 'an image has no ground-truth box (data_loaders/inferred.py:30)',
-    _lib.RN_FLAG_EXCHANGE_TIMEOUT: 'a peer rank did not post its statistics within ~2 s',
+    _lib.RN_FLAG_EXCHANGE_TIMEOUT: 'a peer rank did not post its statistics in time: the statistics (and every '
+                                   'loss / gradient that depends on them) are NaN',
 }
 
 
@@ -83,7 +84,6 @@ class DenseHeadPath(object):
         self.stage_hook = None  # optional callable(stage_name, thunk) -> thunk(); bench.py times stages with it
         self._side = None        # side stream for the detection tail (step(overlap_detect=True))
         self._side_done = None
-        self._stats_fin = None   # statistics snapshot for a loss that is finished on the side stream
         self.pyr = pyramid_for(self.image_size, self.levels, anchor_size_mode, self.names)
         self.anchors = int(self.pyr.anchors_per_image)
         self.rows_total = self.batch * self.anchors
@@ -92,11 +92,23 @@ class DenseHeadPath(object):
 
         dev, B, R, Cn = self.device, self.batch, self.rows_total, self.num_classes
         i32, f32 = torch.int32, torch.float32
-        self.matched = torch.empty((R,), dtype=i32, device=dev)
-        self.label = torch.empty((R,), dtype=i32, device=dev)
-        self.deltas = torch.empty((R, 4), dtype=f32, device=dev)
-        self.iou_max = torch.empty((R,), dtype=f32, device=dev) if keep_iou else None
-        self.stats = torch.zeros((_lib.RN_STATS_HEADER + 3 * Cn,), dtype=torch.float64, device=dev)
+        self._keep_iou = bool(keep_iou)
+        # label buffers (K1 output, K2 input); a second set appears with the first prefetch_assign()
+        self._sets = [None, None]
+        self._cur = 0
+        self._pending = None          # (set index, stats index) of an assignment launched ahead of its step
+        self._assign_stream = None
+        self._assign_done = None
+        self._loss_done = [None, None]   # events after the loss kernels of the last two steps (newest first)
+        # Three statistics vectors used in rotation: step i accumulates into ring[i % 3]; its loss kernel leaves
+        # ring[(i + 2) % 3] zeroed (last used by step i - 1, whose side-stream tail has been waited for by then; the
+        # vector of step i + 1 may already be filling: prefetch_assign), so a training loop needs neither a memset
+        # nor a snapshot copy per step.
+        self._stats_ring = torch.zeros((3, _lib.RN_STATS_HEADER + 3 * Cn), dtype=torch.float64, device=dev)
+        self._stats_clean = [True, True, True]
+        self._stats_i = 0
+        self._static_stats = False   # graph capture: one fixed vector, zeroed by an op of its own
+        self.stats = self._stats_ring[0]
         self.loss_out = torch.zeros((4,), dtype=f32, device=dev)
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._loss_ws_bytes = _lib.lib.rn_loss_workspace_bytes(Cn)
@@ -120,12 +132,25 @@ class DenseHeadPath(object):
         self._nms_ws_bytes = _lib.lib.rn_nms_workspace_bytes(B, Cn, cap)
         self._nms_ws = torch.empty((self._nms_ws_bytes,), dtype=torch.uint8, device=dev)
 
-        self._m_matched = self._merged_maps(self.matched, 4)
-        self._m_label = self._merged_maps(self.label, 4)
-        self._m_deltas = self._merged_maps(self.deltas, 16)
-        self._m_iou = self._merged_maps(self.iou_max, 4)
+        self._use_set(0)
 
     # ---- layout helpers ----------------------------------------------------------------------
+    def _use_set(self, k):
+        """Make label-buffer set k the current one (allocating it on first use)."""
+        if self._sets[k] is None:
+            R, dev = self.rows_total, self.device
+            t = dict(matched=torch.empty((R,), dtype=torch.int32, device=dev),
+                     label=torch.empty((R,), dtype=torch.int32, device=dev),
+                     deltas=torch.empty((R, 4), dtype=torch.float32, device=dev),
+                     iou_max=torch.empty((R,), dtype=torch.float32, device=dev) if self._keep_iou else None)
+            t['maps'] = (self._merged_maps(t['matched'], 4), self._merged_maps(t['label'], 4),
+                         self._merged_maps(t['deltas'], 16), self._merged_maps(t['iou_max'], 4))
+            self._sets[k] = t
+        t = self._sets[k]
+        self._cur = k
+        self.matched, self.label, self.deltas, self.iou_max = t['matched'], t['label'], t['deltas'], t['iou_max']
+        self._m_matched, self._m_label, self._m_deltas, self._m_iou = t['maps']
+
     def _merged_maps(self, tensor, bytes_per_anchor):
         m = _lib.Maps()
         if tensor is not None:
@@ -215,6 +240,31 @@ class DenseHeadPath(object):
             out.p[l] = maps.p[l] + images * h * w * a * bytes_per_anchor if maps.p[l] else None
         return out
 
+    def _rotate_stats(self):
+        """self.stats <- the next vector of the ring, zero (by an earlier loss kernel, else by an op here)."""
+        if not self._static_stats:
+            self._stats_i = (self._stats_i + 1) % 3
+            self.stats = self._stats_ring[self._stats_i]
+        if self._static_stats or not self._stats_clean[self._stats_i]:
+            self.stats.zero_()
+        self._stats_clean[self._stats_i] = False
+
+    def _mark_loss_done(self):
+        """Event after this step's loss kernel: a prefetched assignment of step i + 2 overwrites the label set and
+        reuses the statistics vector this kernel has just read / zeroed."""
+        if self._assign_stream is not None and not torch.cuda.is_current_stream_capturing():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._loss_done = [ev, self._loss_done[0]]
+
+    def _stats_next_ptr(self):
+        """The vector the loss kernel may zero for the next step (None in static mode)."""
+        if self._static_stats:
+            return None
+        nxt = (self._stats_i + 2) % 3
+        self._stats_clean[nxt] = True
+        return _lib.ptr(self._stats_ring[nxt])
+
     def assign(self, gt_boxes, gt_classes, gt_counts, with_flip=False):
         """gt_boxes f32 [B, max_gt, 4], gt_classes i32 [B, max_gt], gt_counts i32 [B] (device).
         Fills self.matched / label / deltas and the label statistics.
@@ -234,7 +284,10 @@ class DenseHeadPath(object):
             raise ValueError('gt_classes must be int32 [%d, %d]' % (B, self.max_gt))
         if tuple(gt_counts.shape) != (B,) or gt_counts.dtype != torch.int32:
             raise ValueError('gt_counts must be int32 [%d]' % B)
-        self.stats.zero_()
+        if self._pending is not None:   # an assignment was launched ahead: this call supersedes it
+            torch.cuda.current_stream().wait_event(self._assign_done)
+            self._pending = None
+        self._rotate_stats()
         gt_boxes, gt_classes, gt_counts = gt_boxes.contiguous(), gt_classes.contiguous(), gt_counts.contiguous()
         self._stage('assign', lambda: _lib.call(
             'rn_assign_encode', C.byref(self.pyr), B, _lib.ptr(gt_boxes), _lib.ptr(gt_classes), _lib.ptr(gt_counts),
@@ -255,10 +308,52 @@ class DenseHeadPath(object):
         self._allreduce('counts')
         return self.label, self.deltas
 
+    def prefetch_assign(self, gt_boxes, gt_classes, gt_counts, with_flip=False):
+        """Launch the NEXT step's assignment now, on its own stream, into the other label-buffer set: K1 is bound
+        by float32 ALU work and the loss kernel by HBM, so the two share the SMs well and the assignment (and, with
+        several GPUs, its count exchange) leaves the step's critical path.  Call it right after `step()` /
+        `loss()` of the current step; the next `step()` (whose ground-truth arguments are then ignored) picks the
+        result up.  The ground-truth tensors must stay unchanged until that step has been issued."""
+        main = torch.cuda.current_stream()
+        if self._static_stats:
+            raise RuntimeError('prefetch_assign is not available on a captured (static) path')
+        if self._pending is not None:
+            main.wait_event(self._assign_done)
+            self._pending = None
+        if self._assign_stream is None:
+            self._assign_stream = torch.cuda.Stream(device=self.device)
+            self._assign_stream.wait_stream(main)        # first use: no per-step events yet
+        elif self._loss_done[1] is not None:
+            self._assign_stream.wait_event(self._loss_done[1])   # loss kernel of the step before the current one
+        else:
+            self._assign_stream.wait_stream(main)
+        cur_set, cur_stats, cur_i = self._cur, self.stats, self._stats_i
+        try:
+            with torch.cuda.stream(self._assign_stream):
+                self._use_set(cur_set ^ 1)
+                self.assign(gt_boxes, gt_classes, gt_counts, with_flip=with_flip)   # rotates the statistics vector
+                self._assign_done = torch.cuda.Event()
+                self._assign_done.record(self._assign_stream)
+            self._pending = (cur_set ^ 1, self._stats_i)
+        finally:   # the current step's buffers stay current until step() switches
+            self._use_set(cur_set)
+            self.stats, self._stats_i = cur_stats, cur_i
+        return self._pending
+
+    def _take_prefetched(self):
+        """Switch to the label set / statistics vector of a prefetched assignment (step() calls this)."""
+        set_k, stats_i = self._pending
+        self._pending = None
+        torch.cuda.current_stream().wait_event(self._assign_done)
+        self._use_set(set_k)
+        self._stats_i = stats_i
+        self.stats = self._stats_ring[stats_i]
+
     # ---- stage 2: loss forward + backward (utils.process_labels_and_logits + losses.loss) ---
     def loss(self, logits, regression, want_grad=True):
         """Returns self.loss_out (device f32 [4]: class loss, regression loss, num_fg, M); the
         gradients w.r.t. the full logits / regression maps land in self.dlogits / self.dreg."""
+        self.join()
         m_logits, logits_t = self._maps(logits, self.num_classes, self._LOGIT_DTYPES)
         m_reg, _ = self._maps(regression, 4)
         st = _lib.stream_ptr()
@@ -269,16 +364,15 @@ class DenseHeadPath(object):
                 'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, dt,
                 _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
             self._allreduce('dice_sums')
+        single = not self._multi_rank()
         self._stage('cls_loss', lambda: _lib.call(
-            'rn_cls_loss_fwd_bwd', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, self.mode,
-            self.focus, self.alpha, self.eps, C.byref(m_dlogits), dt, _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
-            self._loss_ws_bytes, st))
-        self._stage('huber', lambda: _lib.call(
-            'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
-            C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
-            self._huber_ws.numel(), st))
-        self._allreduce('loss_sums')
-        _lib.call('rn_loss_finalize', Cn, self.mode, _lib.ptr(self.stats), _lib.ptr(self.loss_out), st)
+            'rn_head_loss', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode, self.focus,
+            self.alpha, self.eps, C.byref(m_dlogits), dt, C.byref(m_reg), C.byref(self._m_deltas), C.byref(m_dreg),
+            _lib.ptr(self.stats), self._stats_next_ptr(), _lib.ptr(self._loss_ws), self._loss_ws_bytes,
+            _lib.ptr(self.loss_out) if single else None, 0.0, 0, None, _lib.ptr(self.status), None, 0, st))
+        self._mark_loss_done()
+        if not single:
+            self._finish_loss(self.stats)
         return self.loss_out
 
     # ---- stages 2+3 fused: one pass over the logits for the loss AND the candidate selection --
@@ -305,6 +399,7 @@ class DenseHeadPath(object):
             self.loss(logits, regression, want_grad)
             self.select(logits, regression)
             return self.loss_out, self.cand_count
+        self.join()
         m_logits, logits_t = self._maps(logits, self.num_classes, self._LOGIT_DTYPES)
         m_reg, _ = self._maps(regression, 4)
         st = _lib.stream_ptr()
@@ -315,22 +410,16 @@ class DenseHeadPath(object):
                 'rn_cls_sums', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), 0, dt,
                 _lib.ptr(self.stats), _lib.ptr(self._loss_ws), self._loss_ws_bytes, st))
             self._allreduce('dice_sums')
+        # single GPU and nothing deferred: the loss kernel's last CTA also writes the final scalars
+        in_kernel = not self._multi_rank() and not defer_loss
         self._stage('cls_loss', lambda: _lib.call(
-            'rn_cls_loss_select', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode,
-            self.focus, self.alpha, self.eps, C.byref(m_dlogits), dt, _lib.ptr(self.stats), _lib.ptr(self._loss_ws),
-            self._loss_ws_bytes, self.score_thr, self.capacity, _lib.ptr(self.cand_count), _lib.ptr(self.status),
-            _lib.ptr(self._sel_ws), self._sel_ws_bytes, st))
-        self._stage('huber', lambda: _lib.call(
-            'rn_huber_fwd_bwd', C.byref(self.rows), C.byref(m_reg), C.byref(self._m_deltas), C.byref(self._m_label),
-            C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(self.stats), _lib.ptr(self._huber_ws),
-            self._huber_ws.numel(), st))
-        if defer_loss:
-            # snapshot of the statistics: the next step's assignment zeroes self.stats while the side stream still
-            # needs this step's sums (step(overlap_detect=True) finishes the loss there)
-            if self._stats_fin is None:
-                self._stats_fin = torch.empty_like(self.stats)
-            self._stats_fin.copy_(self.stats)
-        else:
+            'rn_head_loss', C.byref(self.rows), Cn, C.byref(m_logits), C.byref(self._m_label), self.mode, self.focus,
+            self.alpha, self.eps, C.byref(m_dlogits), dt, C.byref(m_reg), C.byref(self._m_deltas), C.byref(m_dreg),
+            _lib.ptr(self.stats), self._stats_next_ptr(), _lib.ptr(self._loss_ws), self._loss_ws_bytes,
+            _lib.ptr(self.loss_out) if in_kernel else None, self.score_thr, self.capacity, _lib.ptr(self.cand_count),
+            _lib.ptr(self.status), _lib.ptr(self._sel_ws), self._sel_ws_bytes, st))
+        self._mark_loss_done()
+        if not in_kernel and not defer_loss:
             self._finish_loss(self.stats)
         if finalize:
             self.select_finalize(regression)
@@ -348,6 +437,7 @@ class DenseHeadPath(object):
 
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
+        self.join()
         m_scores, scores_t = self._maps(scores, self.num_classes, self._LOGIT_DTYPES)
         first = scores_t[0] if isinstance(scores_t, (list, tuple)) else scores_t
         fmt = (_lib.RN_SCORES_LOGITS if scores_are_logits else 0) | \
@@ -362,6 +452,7 @@ class DenseHeadPath(object):
         return self.cand_count
 
     def nms(self):
+        self.join()
         self._stage('nms', lambda: _lib.call(
             'rn_nms_classwise', self.batch, self.num_classes, self.capacity, _lib.ptr(self.cand_boxes),
             _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes), _lib.ptr(self.cand_count), self.nms_iou,
@@ -390,7 +481,10 @@ class DenseHeadPath(object):
 
         with_flip=True: the ground truth holds batch/2 images and the batch is the reference's
         `[orig, flipped]` sample (see `assign`)."""
-        self.assign(gt_boxes, gt_classes, gt_counts, with_flip=with_flip)
+        if self._pending is not None:
+            self._take_prefetched()
+        else:
+            self.assign(gt_boxes, gt_classes, gt_counts, with_flip=with_flip)
         if not (fused and self.fused_select_supported()):
             self.join()
             self.loss(logits, regression)
@@ -406,16 +500,23 @@ class DenseHeadPath(object):
             self.select_finalize(regression)
             self.nms()
             return self.loss_out, self.det_count
-        defer = self._can_defer_loss()
+        defer = self._multi_rank() and self._can_defer_loss() and not self._static_stats
         self.loss_and_select(logits, regression, finalize=False, defer_loss=defer)
+        stats_now = self.stats
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device, priority=-1)  # small CTAs first
+        if not torch.cuda.is_current_stream_capturing():
+            # the tail reads the caller's regression tensor on the side stream: keep the caching allocator from
+            # handing its memory to main-stream work before the tail has run
+            for t in (regression.values() if isinstance(regression, dict) else
+                      regression if isinstance(regression, (list, tuple)) else [regression]):
+                t.record_stream(self._side)
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(self._side):
             self._side.wait_event(ready)
             if defer:   # loss-sum exchange + finalize: nothing on the main stream waits for them
-                self._finish_loss(self._stats_fin)
+                self._finish_loss(stats_now)   # this step's ring vector: not reused before the tail is waited for
             self.select_finalize(regression)
             self.nms()
             self._side_done = torch.cuda.Event()
@@ -427,11 +528,15 @@ class DenseHeadPath(object):
         `graph.replay()` then re-runs the step with one launch -- for small workloads (Shapes, VOC, small
         batches) the ~10 kernel launches of a step cost more than the kernels.  Refill the same input
         tensors in place between replays; outputs land in the usual members (loss_out, dlogits, det_*).
-        Single rank only: the peer-memory exchange takes a per-call epoch argument."""
+        Multi-rank: works with the peer-memory exchange (its epochs live in device memory and advance inside the
+        kernel); an NCCL collective is not captured here."""
         if self._multi_rank():
-            raise RuntimeError('DenseHeadPath.capture: graph capture is single-rank (the statistics exchange '
-                               'carries a per-call epoch); call step() instead')
+            self._allreduce('counts', torch.zeros_like(self.stats))   # builds the peer exchange (collective set-up)
+            if self._peer is None or self.exchange == 'nccl':
+                raise RuntimeError('DenseHeadPath.capture with several ranks needs the peer-memory exchange '
+                                   "(exchange='peer'); the NCCL fallback is not captured")
         self.join()
+        self._static_stats = True   # one fixed statistics vector, zeroed by an op inside the graph
         hook, self.stage_hook = self.stage_hook, None
         try:
             side = torch.cuda.Stream(device=self.device)

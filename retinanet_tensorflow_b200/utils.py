@@ -263,11 +263,95 @@ def _anchor_sizes_for(level, image_size, anchor_size_mode='tf1_int_trunc'):
                      np.array(lv.anchor_w[:lv.num_anchors], np.float32)], -1)
 
 
-def postprocess_and_mask(input, trainable_masks, image_size, levels, name='postprocess_and_mask'):
+class _MaskPlan(object):
+    """One scan of the trainable masks (rn_mask_scan), shared by every tensor that is masked with them."""
+
+    def __init__(self, trainable_masks):
+        self.keys = list(trainable_masks.keys())
+        self.masks = [as_cuda(trainable_masks[k], None) for k in self.keys]
+        self.masks = [(m if m.dtype in (torch.bool, torch.uint8) else (m != 0)).contiguous() for m in self.masks]
+        self.rows = _lib.rows_of([int(m.numel()) for m in self.masks])
+        self.mask_maps = _lib.maps_of([m.view(torch.uint8).reshape(-1) for m in self.masks])
+        dev = self.masks[0].device if self.masks else _lib.require_cuda()
+        nbytes = max(int(_lib.lib.rn_mask_workspace_bytes(C.byref(self.rows))), 4)
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        count = torch.zeros((1,), dtype=torch.int64, device=dev)
+        _lib.call('rn_mask_scan', C.byref(self.rows), C.byref(self.mask_maps), _lib.ptr(self.ws), nbytes, _lib.ptr(count),
+                  _lib.stream_ptr())
+        self.count = int(count.item())   # M: the masked tensors have a data-dependent shape, as in the reference
+
+    def gather(self, per_level):
+        """{level: [.., K]} (leading shape = the mask's) -> [M, K], levels concatenated in dict order."""
+        if list(per_level.keys()) != self.keys:
+            raise AssertionError('dict keys differ')   # utils.dict_starmap's assert (utils.py:165)
+        ts = [as_cuda(per_level[k], None) for k in self.keys]
+        tail = tuple(ts[0].shape[self.masks[0].dim():])
+        k = 1
+        for d in tail:
+            k *= int(d)
+        for t, m in zip(ts, self.masks):
+            if tuple(t.shape[:m.dim()]) != tuple(m.shape) or tuple(t.shape[m.dim():]) != tail or t.dtype != ts[0].dtype:
+                raise ValueError('tensor %s does not match its mask %s' % (tuple(t.shape), tuple(m.shape)))
+        out = torch.empty((self.count,) + tail, dtype=ts[0].dtype, device=ts[0].device)
+        if self.count:
+            _lib.call('rn_mask_gather', C.byref(self.rows), k * ts[0].element_size(), C.byref(_lib.maps_of(ts)),
+                      C.byref(self.mask_maps), _lib.ptr(self.ws), _lib.ptr(out), _lib.stream_ptr())
+        return out
+
+
+class _LazyClassification(Classification):
+    """`Classification(unscaled, prob)` whose `prob` is computed on first access.  The reference builds
+    sigmoid(logits) for every level and its masked copy eagerly (utils.py:249,270) although its loss only feeds
+    them to tf.summary.histogram (losses.py:160-163); here they cost nothing until somebody reads them."""
+
+    def __new__(cls, unscaled, make_prob):
+        self = super().__new__(cls, unscaled, None)
+        self._make_prob, self._prob = make_prob, None
+        return self
+
+    @property
+    def prob(self):
+        if self._prob is None:
+            self._prob = self._make_prob()
+        return self._prob
+
+    def __iter__(self):
+        return iter((self.unscaled, self.prob))
+
+    def __getitem__(self, i):
+        return (self.unscaled, self.prob)[i]
+
+
+class _LazyDict(dict):
+    """{level: f(source[level])}, each value computed on first access."""
+
+    def __init__(self, f, source):
+        super().__init__({k: None for k in source})
+        self._f, self._src = f, source
+
+    def __getitem__(self, k):
+        v = super().__getitem__(k)
+        if v is None:
+            v = self._f(self._src[k])
+            super().__setitem__(k, v)
+        return v
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def get(self, k, default=None):
+        return self[k] if k in self else default
+
+
+def postprocess_and_mask(input, trainable_masks, image_size, levels, name='postprocess_and_mask', *, _plan=None):
     """Decode the regressions of every level, then drop the ignored anchors of every level
     (boolean mask over [B, H, W, A], rows ordered b, y, x, a) and concatenate the levels
     (utils.py:258-284).  Compatibility form that materialises the masked tensors exactly like
-    the reference; `pipeline.DenseHeadPath.loss` is the fused form that never does."""
+    the reference (one order-preserving compaction launch per tensor, rn_mask_gather);
+    `pipeline.DenseHeadPath.loss` is the fused form that never does."""
     image_size = host_ints(image_size)
     detection = Detection(
         classification=input['detection']['classifications'],
@@ -275,27 +359,28 @@ def postprocess_and_mask(input, trainable_masks, image_size, levels, name='postp
         regression_postprocessed=dict_starmap(
             lambda r, l: regression_postprocess(r, _anchor_sizes_for(l, image_size)),
             (input['detection']['regressions'], {k: levels[k] for k in input['detection']['regressions']})))
-
-    def masked(d):
-        return merge_outputs(dict_starmap(lambda x, m: as_cuda(x)[as_cuda(m, torch.bool)], (d, trainable_masks)))
-
-    unscaled = detection.classification.unscaled
-    prob = detection.classification.prob
+    plan = _MaskPlan(trainable_masks) if _plan is None else _plan
+    cls = detection.classification
+    if isinstance(cls, _LazyClassification):
+        masked_cls = _LazyClassification(plan.gather(cls.unscaled) if cls.unscaled else None, lambda: plan.gather(cls.prob))
+    else:
+        masked_cls = Classification(unscaled=plan.gather(cls.unscaled) if cls.unscaled else None,
+                                    prob=plan.gather(cls.prob) if cls.prob else None)
     trainable = Detection(
-        classification=Classification(unscaled=masked(unscaled) if unscaled else None,
-                                      prob=masked(prob) if prob else None),
-        regression=masked(detection.regression),
-        regression_postprocessed=masked(detection.regression_postprocessed))
+        classification=masked_cls,
+        regression=plan.gather(detection.regression),
+        regression_postprocessed=plan.gather(detection.regression_postprocessed))
     return {**input, 'detection': detection, 'detection_trainable': trainable}
 
 
 def process_labels_and_logits(labels, logits, levels, name='process_labels_and_logits'):
     """Wrap label maps as probabilities and logits as (unscaled, sigmoid), decode and mask both
-    with the labels' trainable masks (utils.py:240-255)."""
+    with the labels' trainable masks (utils.py:240-255).  The sigmoid maps are evaluated lazily."""
     labels = dict_update(labels, ['detection', 'classifications'], lambda c: Classification(unscaled=None, prob=c))
     logits = dict_update(logits, ['detection', 'classifications'],
-                         lambda c: Classification(unscaled=c, prob=dict_map(sigmoid, c)))
+                         lambda c: _LazyClassification(c, lambda: _LazyDict(sigmoid, c)))
     image_size = list(as_cuda(labels['image'], None).shape[1:3])
-    labels = postprocess_and_mask(labels, labels['trainable_masks'], image_size=image_size, levels=levels)
-    logits = postprocess_and_mask(logits, labels['trainable_masks'], image_size=image_size, levels=levels)
+    plan = _MaskPlan(labels['trainable_masks'])
+    labels = postprocess_and_mask(labels, labels['trainable_masks'], image_size=image_size, levels=levels, _plan=plan)
+    logits = postprocess_and_mask(logits, labels['trainable_masks'], image_size=image_size, levels=levels, _plan=plan)
     return labels, logits

@@ -45,11 +45,12 @@ def make_case(seed):
     mode = str(rng.choice(MODES))
     bf16 = bool(c % 8 == 0 and rng.uniform() < 0.35)
     generic = bool(not bf16 and rng.uniform() < 0.2)
+    head = bool(rng.uniform() < 0.5)   # the one-launch entry point (rn_head_loss) instead of the separate calls
     pred = rng.normal(0, 1.5, (rows, 4)).astype(np.float32)
     target = rng.normal(0, 1.0, (rows, 4)).astype(np.float32)
-    return dict(c=c, seg_rows=seg_rows, lab=lab, x=x, mode=mode, bf16=bf16, generic=generic, pred=pred,
-                target=target, desc='C=%d segs=%s mode=%s bf16=%d generic=%d mu=%.1f sigma=%.1f pos=%.2f ign=%.2f'
-                % (c, seg_rows, mode, bf16, generic, mu, sigma, p_pos, p_ign))
+    return dict(c=c, seg_rows=seg_rows, lab=lab, x=x, mode=mode, bf16=bf16, generic=generic, head=head, pred=pred,
+                target=target, desc='C=%d segs=%s mode=%s bf16=%d generic=%d head=%d mu=%.1f sigma=%.1f pos=%.2f ign=%.2f'
+                % (c, seg_rows, mode, bf16, generic, head, mu, sigma, p_pos, p_ign))
 
 
 def run_case(case):
@@ -92,11 +93,16 @@ def run_case(case):
         if mode_bits & _lib.RN_CLS_DICE_FLAG:
             _lib.call('rn_cls_sums', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, dt, _lib.ptr(stats),
                       _lib.ptr(ws), ws_bytes, st)
-        _lib.call('rn_cls_loss_fwd_bwd', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, mode_bits, 2.0, 0.25, 1e-7,
-                  C.byref(m_dx), dt, _lib.ptr(stats), _lib.ptr(ws), ws_bytes, st)
-        _lib.call('rn_huber_fwd_bwd', C.byref(rows), C.byref(m_pred), C.byref(m_tgt), C.byref(m_lab),
-                  C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(stats), _lib.ptr(hws), hws.numel(), st)
-        _lib.call('rn_loss_finalize', c, mode_bits, _lib.ptr(stats), _lib.ptr(out), st)
+        if case['head']:
+            _lib.call('rn_head_loss', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), mode_bits, 2.0, 0.25, 1e-7,
+                      C.byref(m_dx), dt, C.byref(m_pred), C.byref(m_tgt), C.byref(m_dreg), _lib.ptr(stats), None,
+                      _lib.ptr(ws), ws_bytes, _lib.ptr(out), 0.0, 0, None, None, None, 0, st)
+        else:
+            _lib.call('rn_cls_loss_fwd_bwd', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, mode_bits, 2.0, 0.25,
+                      1e-7, C.byref(m_dx), dt, _lib.ptr(stats), _lib.ptr(ws), ws_bytes, st)
+            _lib.call('rn_huber_fwd_bwd', C.byref(rows), C.byref(m_pred), C.byref(m_tgt), C.byref(m_lab),
+                      C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(stats), _lib.ptr(hws), hws.numel(), st)
+            _lib.call('rn_loss_finalize', c, mode_bits, _lib.ptr(stats), _lib.ptr(out), st)
         torch.cuda.synchronize()
     finally:
         _lib.call('rn_set_option', b'fast_focal', 1)

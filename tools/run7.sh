@@ -1,0 +1,13 @@
+cd $GRAFT_REPO_ROOT
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+V=$PWD/retinanet_tensorflow_b200/lib/variants
+for lib in "" "$V/librndense_k1r56.so"; do
+for flags in "" "--no-pipeline" "--workload crowded" "--workload crowded --no-pipeline"; do
+  RNDENSE_LIB=$lib timeout 300 python bench.py --no-cpu-baseline --steps 60 --warmup 5 --e2e-steps 0 $flags 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print('[$lib $flags] step %.3f ms  %.0f img/s launches %s' % (d['ms_per_step'], d['value'], d.get('gpu_launches')), {k: round(v['ms'], 4) for k, v in d['kernels'].items()}, d['roofline']['frac'])
+"
+done
+done
+timeout 900 python tests/fuzz_loss.py --cases 500 --seed 5 2>&1 | grep -v "cases ok" | tail -12
