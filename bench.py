@@ -49,8 +49,10 @@ def parse_args():
                     help='infer: BASELINE config 4 (decode + top-k per level + per-class NMS only; not the headline metric)')
     ap.add_argument('--topk', type=int, default=1000)
     ap.add_argument('--no-overlap', action='store_true', help='keep the detection tail on the main stream')
-    ap.add_argument('--no-pipeline', action='store_true',
-                    help='run the assignment inside its own step instead of one step ahead on a second stream')
+    ap.add_argument('--pipeline', action='store_true',
+                    help='launch the assignment one step ahead on a second stream (DenseHeadPath.prefetch_assign); '
+                         'measured: no gain on one GPU, the persistent loss kernel leaves no room on the SMs '
+                         '(profiles/r02_schedule.md)')
     ap.add_argument('--cpu-images', type=int, default=None, help='images in the CPU sample (default: one per core)')
     ap.add_argument('--flip', action='store_true',
                     help="the reference's [orig, flipped] batches (dataset.py:182-204): --batch counts source images, the "
@@ -350,7 +352,9 @@ class Harness(object):
         self.stage_events = None
         self.graph = None
         self.overlap = not args.no_overlap
-        self.pipeline = not args.no_pipeline
+        # several GPUs: launching the assignment one step ahead takes its count exchange off the critical path (+1.6 % at
+        # N = 2); one GPU: no gain (profiles/r02_schedule.md), so it stays opt-in there
+        self.pipeline = bool(args.pipeline) or world > 1
 
     def reseed(self, sigma, seed_base=1000):
         """Same labels, new head outputs with another background spread (in place of the old ones)."""

@@ -40,6 +40,9 @@ namespace rn {
 #ifndef RN_TILE_MINB
 #define RN_TILE_MINB 2
 #endif
+#ifndef RN_TILE_BOUND_THREADS
+#define RN_TILE_BOUND_THREADS (RN_TILE_CWARPS * 32 + 32)
+#endif
 constexpr int kConsumerWarps = RN_TILE_CWARPS;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kTileThreads = kConsumerThreads + 32;   // + one producer warp
@@ -361,7 +364,7 @@ struct __align__(16) QEntry {
 // MODE: RN_CLS_FOCAL (focus 2) | RN_CLS_BCE | RN_CLS_BALANCED_BCE | RN_CLS_NONE; DICE adds the dice gradient.
 // SELECT: fused candidate pre-selection.  BF16: bf16x8 units.  DENSE: float labels [rows, C], all rows trainable.
 template <int MODE, bool DICE, bool SELECT, bool BF16, bool DENSE>
-__global__ void __launch_bounds__(kTileThreads, RN_TILE_MINB)
+__global__ void __launch_bounds__(RN_TILE_BOUND_THREADS, RN_TILE_MINB)
 cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileDev prm) {
   extern __shared__ __align__(128) unsigned char smem[];
   // [0,64) full barriers, [64,128) empty barriers, [128,256) tile info, then tables, queues, stages
@@ -402,6 +405,7 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
         da = (float)(-2.0 / ((double)C * U));
         db = (float)(2.0 * I / ((double)C * U * U));
       }
+      if (!(M > 0)) wn = wp = da = db = 0.0f;   // every row ignored: 0/0 weights must not leak into the (zero) gradients
       s_tab[c] = wn;
       s_tab[C + c] = wp;
       s_tab[2 * C + c] = da;
@@ -806,6 +810,13 @@ int launch_cls_tile(const Segs& segs, const TileParams& tp, int mode, bool selec
   if (tr < 1) tr = 1;
   if (tr > (unsigned)kMaxTileRows) tr = kMaxTileRows;
   if (tr >= 4) tr &= ~3u;
+  // prefer a tile whose units divide evenly among the consumer threads (every thread then does the same number of
+  // units per tile): look a little below the byte budget for such a row count
+  for (unsigned r = tr; r >= 4 && r * 8u >= tr * 7u; r -= 4)
+    if ((r * dev.cv) % (unsigned)kConsumerThreads == 0) {
+      tr = r;
+      break;
+    }
   dev.tile_rows = tr;
   unsigned long long tiles = 0;
   for (int i = 0; i < RN_MAX_LEVELS; ++i) {

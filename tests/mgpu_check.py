@@ -43,7 +43,30 @@ def run(wl, first, count, group, mode, logits=None, regs=None):
             torch.equal(path.dlogits, want[2])):
         raise SystemExit('MISMATCH overlapped step vs serial step (%s): %s vs %s' % (
             mode, path.loss_out.tolist(), want[0].tolist()))
+    # the assignment launched one step ahead on its own stream (count exchange included) gives the same step
+    for lg in (other, logits):
+        path.step(gb, gc, gn, lg, regs, overlap_detect=True)
+        path.prefetch_assign(gb, gc, gn)
+    path.join()
+    torch.cuda.synchronize()
+    if not (torch.equal(path.loss_out, want[0]) and torch.equal(path.det_count, want[1]) and
+            torch.equal(path.dlogits, want[2])):
+        raise SystemExit('MISMATCH prefetched assignment vs serial step (%s): %s vs %s' % (
+            mode, path.loss_out.tolist(), want[0].tolist()))
     path.check_status(ignore=12)
+    # the whole multi-rank step as ONE CUDA graph (the exchange epochs live in device memory): replays reproduce it
+    if path._peer is not None and path.exchange != 'nccl':
+        gpath = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, count, wl.max_gt, cls_mode=mode,
+                              process_group=group, capacity=8192, exchange='peer')
+        graph = gpath.capture(gb, gc, gn, logits, regs)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        if not (torch.equal(gpath.loss_out, want[0]) and torch.equal(gpath.det_count, want[1]) and
+                torch.equal(gpath.dlogits, want[2])):
+            raise SystemExit('MISMATCH graph replay vs eager step (%s): %s vs %s' % (
+                mode, gpath.loss_out.tolist(), want[0].tolist()))
+        gpath.check_status(ignore=12)
     return path, logits, regs
 
 

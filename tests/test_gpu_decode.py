@@ -107,7 +107,7 @@ def test_select_and_nms_exact_on_identical_inputs(name, batch):
     assert total > 0
 
 
-@pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2)])
+@pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2), ('coco', 1), ('crowded', 1)])
 def test_fused_select_from_logits_and_deltas(name, batch):
     """The fused path (sigmoid and decode inside the kernels) selects exactly what the
     two-step path selects, and its values agree with the oracle's float32 math."""

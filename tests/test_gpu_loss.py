@@ -41,12 +41,21 @@ def focal_kernel(request):
     _lib.call('rn_set_option', b'fast_focal', 1)
 
 
+def _outside_pure_rtol(got, want, rtol=1e-5):
+    """Fraction of elements that a PURE relative tolerance (no absolute floor) rejects, among the non-zero ones."""
+    nz = want != 0
+    bad = np.abs(got.astype(np.float64) - want.astype(np.float64)) > rtol * np.abs(want.astype(np.float64))
+    return float((bad & nz).sum()) / max(int(nz.sum()), 1)
+
+
 @pytest.mark.parametrize('mode', MODES)
-@pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2)])
+@pytest.mark.parametrize('name,batch', [('shapes', 2), ('voc', 2), ('coco', 1), ('crowded', 1)])
 def test_fused_loss_matches_oracle(name, batch, mode, focal_kernel):
     import torch
     if focal_kernel == 0 and (mode != 'focal' or name == 'shapes'):
         pytest.skip('the generic kernel is what runs anyway')
+    if name in ('coco', 'crowded') and mode not in ('focal', 'bce_dice'):
+        pytest.skip('the headline shapes run the two modes the bench reports')
     wl, path, cls, mask, reg, logits, regs = _setup(name, batch, mode)
     out = path.loss(logits.cuda(), regs.cuda()).cpu().numpy()
     torch.cuda.synchronize()
@@ -61,8 +70,14 @@ def test_fused_loss_matches_oracle(name, batch, mode, focal_kernel):
     # gradients w.r.t. the full maps: zero on ignored anchors (boolean_mask's gradient)
     g_ref = np.zeros_like(x)
     g_ref[mask] = oracle.classification_loss_grad(cls[mask], x[mask], fg, mode=mode)
-    helpers.assert_close(path.dlogits.cpu().numpy(), g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max(),
-                         what='dlogits ' + mode)
+    g = path.dlogits.cpu().numpy()
+    helpers.assert_close(g, g_ref, rtol=1e-5, atol=1e-6 * np.abs(g_ref).max(), what='dlogits ' + mode)
+    # how many elements need the absolute floor at all (the reference's `1 - (1 - p)` quantisation, DESIGN.md
+    # section 2): a small fraction, and the same for the streaming kernel (ex2/rcp.approx) and the libm one
+    frac = _outside_pure_rtol(g, g_ref)
+    print('PARITY %s batch %d %s kernel=%s: %.4f %% of the non-zero gradient elements outside pure rtol 1e-5'
+          % (name, batch, mode, 'generic' if focal_kernel == 0 else 'streaming', 100 * frac))
+    assert frac < 0.05
     gr_ref = np.zeros_like(r)
     gr_ref[mask] = oracle.regression_loss_grad(reg[mask], r[mask], fg)
     helpers.assert_close(path.dreg.cpu().numpy(), gr_ref, rtol=1e-5, atol=1e-6 * np.abs(gr_ref).max(), what='dreg')

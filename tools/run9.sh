@@ -1,0 +1,11 @@
+cd $GRAFT_REPO_ROOT
+python tools/overlap_probe.py coco 2>&1 | head -16
+for flags in "" "--no-pipeline" "--workload crowded" "--workload crowded --no-pipeline"; do
+  timeout 300 python bench.py --no-cpu-baseline --quick --steps 100 --warmup 5 --e2e-steps 3 $flags 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+print('[$flags] step %.3f ms  %.0f img/s launches %s' % (d['ms_per_step'], d['value'], d.get('gpu_launches')), {k: round(v['ms'], 4) for k, v in d['kernels'].items()}, d['roofline']['frac'])
+"
+done
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
+timeout 900 python tests/fuzz_loss.py --cases 500 --seed 5 2>&1 | grep -v "cases ok" | tail -12
