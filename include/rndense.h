@@ -114,6 +114,8 @@ typedef struct rn_maps {
 #define RN_CLS_BCE 2          /* mean(BCE)                              losses.py:124-125      */
 #define RN_CLS_BALANCED_BCE 3 /* mean(balanced BCE, axis=0)             losses.py:96-110,127   */
 #define RN_CLS_DICE_FLAG 16   /* + mean_C(dice(smooth=0, axis=0))       losses.py:50-60,130    */
+#define RN_CLS_GENERIC_FLAG 32 /* per call: take the generic kernel (libm, IEEE division, any C / focus) even where the
+                                 streaming kernel applies -- the parity tests run both; no process-global switch */
 
 /* element type of the logits / dlogits maps of the classification-loss entry points */
 #define RN_DTYPE_F32 0

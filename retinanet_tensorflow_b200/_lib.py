@@ -20,6 +20,7 @@ RN_LABEL_IGNORE = -2
 
 RN_CLS_NONE, RN_CLS_FOCAL, RN_CLS_BCE, RN_CLS_BALANCED_BCE = 0, 1, 2, 3
 RN_CLS_DICE_FLAG = 16
+RN_CLS_GENERIC_FLAG = 32
 RN_DTYPE_F32, RN_DTYPE_BF16 = 0, 1
 RN_SCORES_LOGITS, RN_SCORES_BF16 = 1, 2
 

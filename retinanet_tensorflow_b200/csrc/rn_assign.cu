@@ -29,10 +29,7 @@ struct AssignParams {
   int tpc;  // threads per cell
 };
 
-#ifndef RN_ASSIGN_MAXNREG
-#define RN_ASSIGN_MAXNREG 48
-#endif
-__global__ void __maxnreg__(RN_ASSIGN_MAXNREG)   // two CTAs must fit beside the resident loss kernel (prefetch_assign), see DESIGN.md
+__global__ void __launch_bounds__(kTileH * kTileW * 6)
 
 assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ AssignParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -151,8 +148,24 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
   // ---- IoU scan (utils.iou, utils.py:70-92), strict '>' keeps the first maximum.  The IEEE
   // division only runs when the pair can beat the running best: rcp.approx bounds the quotient
   // to 4e-7 relative, so `approx * (1 + 2e-6) <= best` proves fl(inter / uni) <= best.
+  // Two cheap rejections before the per-anchor work (a rejected pair has IoU == 0, which can neither win nor
+  // tie above 0, so skipping it cannot change the arg-max or its first-maximum rule):
+  //   * per warp: the union of the warp's anchor boxes (shuffle-reduced once) against the GT -- uniform branch;
+  //   * per thread: the thread's three anchors are concentric (one aspect ratio, three scales), so a GT that
+  //     misses the hull of the three misses all of them.
+  float h0 = a0[0], h1 = a1[0], h2 = a2[0], h3 = a3[0];
+#pragma unroll
+  for (int k = 1; k < kApt; ++k) {
+    h0 = fminf(h0, a0[k]);
+    h1 = fminf(h1, a1[k]);
+    h2 = fmaxf(h2, a2[k]);
+    h3 = fmaxf(h3, a3[k]);
+  }
+  const float w0 = warp_min(h0), w1 = warp_min(h1), w2 = warp_max(h2), w3 = warp_max(h3);
   for (int j = 0; j < n_kept; ++j) {
     const float4 g = s_box[j];
+    if (g.z < w0 || g.x > w2 || g.w < w1 || g.y > w3) continue;   // misses every anchor of this warp
+    if (g.z < h0 || g.x > h2 || g.w < h1 || g.y > h3) continue;   // misses this thread's anchors
     const float ga = s_area[j];
 #pragma unroll
     for (int k = 0; k < kApt; ++k) {

@@ -175,6 +175,7 @@ cls_loss_kernel(const __grid_constant__ Segs segs, const __grid_constant__ ClsPa
   }
 }
 
+// Arguments of the streaming classification-loss kernel as the entry points below assemble them
 struct FastParams {
   Ptrs logits, label, dlogits;
   float alpha, eps;
@@ -197,335 +198,6 @@ struct FastParams {
   int32_t* sel_count;    // [B]
   uint32_t* status;
 };
-
-
-// Per-thread state of the fast kernel that both the hot loop and the rare path need.
-struct FastCtx {
-  const float* s_tab;   // [4][C] w_neg, w_pos, dice A, dice B (shared memory)
-  int C;
-  float eps, cg, inv_fg, inv_mc, alpha;
-};
-
-// ---- rare path (noinline keeps it out of the hot loop's register allocation) -----------------------
-// Handles one float4 unit that is not "four confident negatives": hard negatives, the row's positive
-// element, and -- when SELECT -- the candidate pre-selection.  Returns the four loss partials in l
-// (focal: w^2 log(.) terms of negatives; the positive's full loss goes to acc_pos).
-struct UnitOut {
-  float4 g, l;
-  float pos;   // focal: the positive element's own loss (summed separately, it has no -(1-alpha) factor)
-};
-
-template <int MODE, bool DICE, bool SELECT>
-__device__ __noinline__ UnitOut fast_slow_unit(FastCtx cx, const FastParams& prm, const Segs& segs, int s,
-                                               unsigned row, unsigned c4, int lab, float4 v) {
-  UnitOut out;
-  out.pos = 0.f;
-  float4& g = out.g;
-  float4& l = out.l;
-  const float xs[4] = {v.x, v.y, v.z, v.w};
-  if (SELECT) {
-    float bp = -INFINITY;
-    int bc = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (xs[k] > prm.sel_trigger) {
-        const float pk = sigmoid_f32(xs[k]);
-        if (pk > bp) {
-          bp = pk;
-          bc = (int)c4 + k;
-        }
-      }
-    }
-    if (bp > prm.sel_thr) {
-      const unsigned per_image = (unsigned)(segs.rows[s] / prm.sel_images);
-      const unsigned bimg = row / per_image;
-      const int anchor = (int)(segs.start[s] / prm.sel_images) + (int)(row - bimg * per_image);
-      const int slot = reserve_slot(prm.sel_count, (int)bimg, prm.sel_capacity);
-      if (slot < prm.sel_capacity) {
-        const size_t o = (size_t)bimg * prm.sel_capacity + slot;
-        prm.sel_anchor[o] = anchor;
-        prm.sel_score[o] = bp;
-        prm.sel_class[o] = bc;
-      } else {
-        raise_flag(prm.status, RN_FLAG_CAND_OVERFLOW);
-      }
-    }
-  }
-  g = make_float4(0.f, 0.f, 0.f, 0.f);
-  l = g;
-  if (lab == RN_LABEL_IGNORE) return out;
-  const unsigned d = (unsigned)(lab - (int)c4);
-  const float* s_wneg = cx.s_tab;
-  const float* s_wpos = cx.s_tab + cx.C;
-  const float* s_da = cx.s_tab + 2 * cx.C;
-  const float* s_db = cx.s_tab + 3 * cx.C;
-  float ls[4], gs[4];
-  if constexpr (MODE == RN_CLS_FOCAL) {
-    LossScalars sc;
-    sc.focus = 2.0f;
-    sc.alpha = cx.alpha;
-    sc.one_minus_alpha = 1.0f - cx.alpha;
-    sc.eps = cx.eps;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float pq;
-      ls[k] = focal_neg_fast(xs[k], cx.eps, cx.cg, gs[k], pq);
-      if (d == (unsigned)k) {  // the row's positive class: redo this element with z = 1
-        float lp, gp;
-        focal_elem<true>(xs[k], true, sc, lp, gp);
-        gp *= cx.inv_fg;
-        out.pos += lp;
-        if (DICE) gp += s_da[c4 + k] * pq;
-        ls[k] = 0.f;
-        gs[k] = gp;
-      }
-      if (DICE) gs[k] = fmaf(s_db[c4 + k], pq, gs[k]);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float z = (d == (unsigned)k) ? 1.0f : 0.0f;
-      float loss = 0.f, pk = 0.f, dx = 0.f;
-      bce_elem<true>(xs[k], z, loss, pk, dx);
-      float gk = 0.f;
-      if (MODE == RN_CLS_NONE) {
-        loss = 0.f;
-      } else {
-        float wk = 1.0f;
-        if (MODE == RN_CLS_BALANCED_BCE) wk = z == 1.0f ? s_wpos[c4 + k] : s_wneg[c4 + k];
-        loss *= wk;
-        gk = dx * (cx.inv_mc * wk);
-      }
-      if (DICE) gk += (z * s_da[c4 + k] + s_db[c4 + k]) * (pk * (1.0f - pk));
-      ls[k] = loss;
-      gs[k] = gk;
-    }
-  }
-  l = make_float4(ls[0], ls[1], ls[2], ls[3]);
-  g = make_float4(gs[0], gs[1], gs[2], gs[3]);
-  return out;
-}
-
-// ---- hot path: four confident negatives (every logit <= -0.70, no positive in the unit) --------------
-template <int MODE, bool DICE>
-__device__ __forceinline__ void fast_bulk_unit(const FastCtx cx, unsigned c4, float4 v, float4& g, float4& l) {
-  if constexpr (MODE == RN_CLS_FOCAL) {
-    float pq0, pq1, pq2, pq3;
-    l.x = focal_neg_bulk(v.x, cx.eps, cx.cg, g.x, pq0);
-    l.y = focal_neg_bulk(v.y, cx.eps, cx.cg, g.y, pq1);
-    l.z = focal_neg_bulk(v.z, cx.eps, cx.cg, g.z, pq2);
-    l.w = focal_neg_bulk(v.w, cx.eps, cx.cg, g.w, pq3);
-    if (DICE) {
-      const float4 db = *reinterpret_cast<const float4*>(cx.s_tab + 3 * cx.C + c4);
-      g.x = fmaf(db.x, pq0, g.x);
-      g.y = fmaf(db.y, pq1, g.y);
-      g.z = fmaf(db.z, pq2, g.z);
-      g.w = fmaf(db.w, pq3, g.w);
-    }
-  } else {
-    float4 wn = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (MODE == RN_CLS_BALANCED_BCE) wn = *reinterpret_cast<const float4*>(cx.s_tab + c4);
-    float p0, p1, p2, p3;
-    l.x = bce_neg_bulk(v.x, p0);
-    l.y = bce_neg_bulk(v.y, p1);
-    l.z = bce_neg_bulk(v.z, p2);
-    l.w = bce_neg_bulk(v.w, p3);
-    if (MODE == RN_CLS_NONE) {
-      l = make_float4(0.f, 0.f, 0.f, 0.f);
-      g = l;
-    } else {
-      g.x = p0 * (cx.inv_mc * wn.x);
-      g.y = p1 * (cx.inv_mc * wn.y);
-      g.z = p2 * (cx.inv_mc * wn.z);
-      g.w = p3 * (cx.inv_mc * wn.w);
-      if (MODE == RN_CLS_BALANCED_BCE) {
-        l.x *= wn.x; l.y *= wn.y; l.z *= wn.z; l.w *= wn.w;
-      }
-    }
-    if (DICE) {
-      const float4 db = *reinterpret_cast<const float4*>(cx.s_tab + 3 * cx.C + c4);
-      g.x = fmaf(db.x, p0 * (1.0f - p0), g.x);
-      g.y = fmaf(db.y, p1 * (1.0f - p1), g.y);
-      g.z = fmaf(db.z, p2 * (1.0f - p2), g.z);
-      g.w = fmaf(db.w, p3 * (1.0f - p3), g.w);
-    }
-  }
-}
-
-// MODE: RN_CLS_FOCAL (focus 2) | RN_CLS_BCE | RN_CLS_BALANCED_BCE | RN_CLS_NONE; DICE adds the dice
-// gradient (z A_c + B_c) p (1-p).  Compact labels, C % 4 == 0.
-// FIXED_COL: the grid stride is a multiple of the row length, so a thread's float4 column never
-// changes and its row advances by a constant (no wrap test in the loop).
-// BF16: logits and gradients are bfloat16 (a unit is 8 logits = one 128-bit access, "bf16x8"); the math
-// stays float32.  C % 8 == 0.
-template <int MODE, bool DICE, int MINB, bool SELECT, bool FIXED_COL, bool BF16>
-__global__ void __launch_bounds__(kLossThreads, MINB)
-cls_fast_kernel(const __grid_constant__ Segs segs, const __grid_constant__ FastParams prm) {
-  extern __shared__ __align__(16) float s_tab[];   // [4][C]: w_neg, w_pos, dice A, dice B (when needed)
-  __shared__ double s_red[32];
-  constexpr bool kTables = DICE || MODE == RN_CLS_BALANCED_BCE;
-  const int C = prm.num_classes;
-  const double nfg = prm.stats[RN_STAT_NUM_FG];
-  const double M = prm.stats[RN_STAT_TRAINABLE];
-  FastCtx cx;
-  cx.s_tab = s_tab;
-  cx.C = C;
-  cx.eps = prm.eps;
-  cx.alpha = prm.alpha;
-  cx.inv_fg = (float)(1.0 / fmax(nfg, 1.0));
-  cx.inv_mc = M > 0 ? (float)(1.0 / (M * (double)C)) : 0.0f;
-  cx.cg = (1.0f - prm.alpha) * cx.inv_fg;
-  if (kTables) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double npos = prm.stats[RN_STAT_NPOS(c)];
-      float wn = 1.0f, wp = 1.0f, da = 0.0f, db = 0.0f;
-      if (MODE == RN_CLS_BALANCED_BCE) {  // losses.py:99-103, axis=0
-        wp = (float)((M - npos) / M);
-        wn = (float)(npos / M);
-      }
-      if (DICE) {  // d/dp [1 - 2I/U] / C = z A + B,  A = -2/(C U), B = 2 I/(C U^2)
-        const double I = prm.stats[RN_STAT_INTER(C, c)];
-        const double U = npos + prm.stats[RN_STAT_PSUM(C, c)];
-        da = (float)(-2.0 / ((double)C * U));
-        db = (float)(2.0 * I / ((double)C * U * U));
-      }
-      s_tab[c] = wn;
-      s_tab[C + c] = wp;
-      s_tab[2 * C + c] = da;
-      s_tab[3 * C + c] = db;
-    }
-    __syncthreads();
-  }
-  const unsigned cv = (unsigned)prm.cv;
-  const unsigned gstride = gridDim.x * blockDim.x;
-  const unsigned drow = gstride / cv, dcol = gstride % cv;   // dcol == 0 when FIXED_COL
-  const bool write_grad = prm.write_grad != 0;
-  const float trig = SELECT ? prm.sel_trigger : INFINITY;
-  double acc_neg = 0.0, acc_pos = 0.0;
-
-  using Unit = uint4;   // 16 bytes: float4 (4 logits) or bf16x8 (8 logits)
-  constexpr unsigned kPerUnit = BF16 ? 8u : 4u;
-  for (int s = 0; s < segs.num; ++s) {
-    const unsigned units = (unsigned)segs.rows[s] * cv;   // < 2^32 - 2^24, checked by the host
-    const Unit* __restrict__ xin = reinterpret_cast<const Unit*>(prm.logits.p[s]);
-    const int32_t* __restrict__ lab_p = reinterpret_cast<const int32_t*>(prm.label.p[s]);
-    Unit* __restrict__ gout = reinterpret_cast<Unit*>(prm.dlogits.p[s]);
-    unsigned u = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned row = u / cv;          // one division per thread per segment
-    unsigned col = u - row * cv;
-    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);   // four short float accumulators
-
-    // four logits of one row: classify, compute
-    // `full_warp`: all 32 lanes are here (main loop), so the bulk/careful choice is made per warp: when any
-    // lane needs the careful path every lane takes it (it is valid for all units) instead of running both
-    // paths one after the other under divergence.
-    auto do_quad = [&](unsigned rr, unsigned c4, const float4& v, int lab, float4& g, bool full_warp) {
-      float4 l;
-      const float xmax = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-      const bool plain = xmax <= -0.70f && (unsigned)(lab - (int)c4) >= 4u;   // also true for IGNORE (< 0)
-      bool bulk = plain && xmax <= trig;
-      if (full_warp) bulk = __all_sync(0xffffffffu, bulk);
-      if (bulk) {
-        if (lab != RN_LABEL_IGNORE) {
-          fast_bulk_unit<MODE, DICE>(cx, c4, v, g, l);
-          acc4.x += l.x; acc4.y += l.y; acc4.z += l.z; acc4.w += l.w;
-        } else {
-          g = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-        const UnitOut o = fast_slow_unit<MODE, DICE, SELECT>(cx, prm, segs, s, rr, c4, lab, v);
-        g = o.g;
-        acc4.x += o.l.x; acc4.y += o.l.y; acc4.z += o.l.z; acc4.w += o.l.w;
-        acc_pos += (double)o.pos;
-      }
-    };
-    // one 16-byte unit
-    auto do_unit = [&](unsigned uu, unsigned rr, unsigned cc, const Unit& raw, int lab, bool full_warp) {
-      Unit out;
-      if constexpr (BF16) {
-        float4 lo, hi, glo, ghi;
-        unpack_bf16x8(raw, lo, hi);
-        do_quad(rr, cc * 8u, lo, lab, glo, full_warp);
-        do_quad(rr, cc * 8u + 4u, hi, lab, ghi, full_warp);
-        out = pack_bf16x8(glo, ghi);
-      } else {
-        float4 g;
-        do_quad(rr, cc * 4u, *reinterpret_cast<const float4*>(&raw), lab, g, full_warp);
-        out = *reinterpret_cast<const Unit*>(&g);
-      }
-      if (write_grad) __stcs(gout + uu, out);
-    };
-
-    // main loop: four units per iteration, all loads first, no bounds tests
-    // (u + 4*gstride cannot wrap: units + 2^24 < 2^32 is part of the host-side check)
-    // (u | 31) is the warp's last lane (u - lane and gstride are multiples of 32): the condition is the same
-    // for all 32 lanes, which the __all_sync in do_quad relies on
-    while ((u | 31u) + 3u * gstride < units) {
-      unsigned r1, r2, r3, c1, c2, c3;
-      if (FIXED_COL) {
-        r1 = row + drow; r2 = r1 + drow; r3 = r2 + drow;
-        c1 = c2 = c3 = col;
-      } else {
-        c1 = col + dcol; r1 = row + drow; if (c1 >= cv) { c1 -= cv; r1 += 1; }
-        c2 = c1 + dcol;  r2 = r1 + drow;  if (c2 >= cv) { c2 -= cv; r2 += 1; }
-        c3 = c2 + dcol;  r3 = r2 + drow;  if (c3 >= cv) { c3 -= cv; r3 += 1; }
-      }
-      const Unit v0 = __ldcs(xin + u);
-      const Unit v1 = __ldcs(xin + u + gstride);
-      const Unit v2 = __ldcs(xin + u + 2u * gstride);
-      const Unit v3 = __ldcs(xin + u + 3u * gstride);
-      const int l0 = __ldg(lab_p + row);
-      const int l1 = __ldg(lab_p + r1);
-      const int l2 = __ldg(lab_p + r2);
-      const int l3 = __ldg(lab_p + r3);
-      do_unit(u, row, col, v0, l0, true);
-      do_unit(u + gstride, r1, c1, v1, l1, true);
-      do_unit(u + 2u * gstride, r2, c2, v2, l2, true);
-      do_unit(u + 3u * gstride, r3, c3, v3, l3, true);
-      u += 4u * gstride;
-      if (FIXED_COL) {
-        row = r3 + drow;
-      } else {
-        col = c3 + dcol; row = r3 + drow; if (col >= cv) { col -= cv; row += 1; }
-      }
-    }
-    // tail: the last few units of each lane
-    for (; u < units; u += gstride) {
-      const Unit v = __ldcs(xin + u);
-      const int lab = __ldg(lab_p + row);
-      do_unit(u, row, col, v, lab, false);
-      col += dcol;
-      row += drow;
-      if (col >= cv) {
-        col -= cv;
-        row += 1;
-      }
-    }
-    (void)kPerUnit;
-    acc_neg += ((double)acc4.x + (double)acc4.y) + ((double)acc4.z + (double)acc4.w);
-  }
-  // focal: negatives accumulated w^2 log(q+eps), loss = -(1-alpha) * that; BCE modes: plain sum
-  double acc = MODE == RN_CLS_FOCAL ? acc_pos - (double)(1.0f - prm.alpha) * acc_neg : acc_pos + acc_neg;
-
-  acc = block_sum(acc, s_red);
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) {
-    prm.partials[blockIdx.x] = acc;
-    __threadfence();
-    s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    double v = 0.0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += __ldcg(prm.partials + i);
-    v = block_sum(v, s_red);
-    if (threadIdx.x == 0) {
-      prm.stats_out[RN_STAT_CLS_SUM] = v;
-      *prm.ticket = 0;
-    }
-  }
-}
 
 // ---- per-class sums for dice: I_c = sum z p, P_c = sum p (losses.py:53-56) ---------------------
 struct SumsParams {
@@ -1108,10 +780,6 @@ __global__ void sigmoid_kernel(long long n, const float* __restrict__ in, float*
     out[i] = sigmoid_f32(in[i]);
 }
 
-// rn_set_option("fast_focal", 0) forces the generic kernel (used by the parity tests to cover both)
-static int g_fast_kernels = 1;
-// rn_set_option("tile_kernel", 0) selects the round-1 register-streaming kernel (A/B measurements)
-static int g_tile_kernel = 1;
 
 // Persistent grid: exactly the number of CTAs that are resident at once (one full wave), so a
 // grid-stride loop never runs a partially filled second wave.
@@ -1172,84 +840,33 @@ static void launch_cls2(bool dense, bool vec4, unsigned grid, size_t smem, cudaS
     launch_cls<MODE, DICE, false>(vec4, grid, smem, st, segs, prm);
 }
 
-template <int MODE, bool DICE, bool BF16>
-static void launch_fast_variant(const Segs& segs, const FastParams& fp, bool select, long long work,
-                                size_t smem, cudaStream_t st) {
-  // 4 resident CTAs of 256 threads per SM (64 registers): measured faster than 5 x 48 registers.
-  // The grid is the resident wave, rounded down to a multiple of cv / gcd(cv, 256) when that costs
-  // < 4 % of the CTAs, which makes every thread's float4 column constant (FIXED_COL).
-#define RN_LAUNCH_FF(SEL)                                                                                       \
-  do {                                                                                                          \
-    unsigned g = persistent_grid(cls_fast_kernel<MODE, DICE, 4, SEL, false, BF16>, kLossThreads, smem, work);   \
-    const unsigned q = (unsigned)fp.cv / gcd_u((unsigned)fp.cv, (unsigned)kLossThreads);                        \
-    const unsigned gf = g / q * q;                                                                              \
-    if (gf > 0 && (g - gf) * 25u <= g) {                                                                        \
-      cls_fast_kernel<MODE, DICE, 4, SEL, true, BF16><<<gf, kLossThreads, smem, st>>>(segs, fp);                \
-    } else {                                                                                                    \
-      cls_fast_kernel<MODE, DICE, 4, SEL, false, BF16><<<g, kLossThreads, smem, st>>>(segs, fp);                \
-    }                                                                                                           \
-  } while (0)
-  if (select) RN_LAUNCH_FF(true); else RN_LAUNCH_FF(false);
-#undef RN_LAUNCH_FF
-}
-
+// The streaming (tile) kernel for compact labels; `units` is unused (kept for the call sites' symmetry).
 static int launch_fast(const Segs& segs, const FastParams& fp, int mode, bool select, long long units,
                              cudaStream_t st) {
-  if (g_tile_kernel && cls_tile_supported(fp.num_classes, fp.bf16 != 0, false)) {
-    TileParams tp;
-    memset(&tp, 0, sizeof(tp));
-    tp.logits = fp.logits;
-    tp.label = fp.label;
-    tp.dlogits = fp.dlogits;
-    tp.alpha = fp.alpha;
-    tp.eps = fp.eps;
-    tp.stats = fp.stats;
-    tp.stats_out = fp.stats_out;
-    tp.workspace = fp.ticket;
-    tp.num_classes = fp.num_classes;
-    tp.bf16 = fp.bf16;
-    tp.write_grad = fp.write_grad;
-    tp.sel_trigger = fp.sel_trigger;
-    tp.sel_thr = fp.sel_thr;
-    tp.sel_images = fp.sel_images;
-    tp.sel_capacity = fp.sel_capacity;
-    tp.sel_anchor = fp.sel_anchor;
-    tp.sel_score = fp.sel_score;
-    tp.sel_class = fp.sel_class;
-    tp.sel_count = fp.sel_count;
-    tp.status = fp.status;
-    return launch_cls_tile(segs, tp, mode, select, st);
-  }
-  const long long work = (units + 3) / 4;
-  const int base = mode & 15;
-  const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
-  const size_t smem = (dice || base == RN_CLS_BALANCED_BCE) ? 4 * (size_t)fp.num_classes * sizeof(float) : 0;
-#define RN_FAST_MODES(BF)                                                                            \
-  switch (base) {                                                                                      \
-    case RN_CLS_FOCAL:                                                                                 \
-      if (dice) launch_fast_variant<RN_CLS_FOCAL, true, BF>(segs, fp, select, work, smem, st);         \
-      else launch_fast_variant<RN_CLS_FOCAL, false, BF>(segs, fp, select, work, smem, st);             \
-      break;                                                                                           \
-    case RN_CLS_BCE:                                                                                   \
-      if (dice) launch_fast_variant<RN_CLS_BCE, true, BF>(segs, fp, select, work, smem, st);           \
-      else launch_fast_variant<RN_CLS_BCE, false, BF>(segs, fp, select, work, smem, st);               \
-      break;                                                                                           \
-    case RN_CLS_BALANCED_BCE:                                                                          \
-      if (dice) launch_fast_variant<RN_CLS_BALANCED_BCE, true, BF>(segs, fp, select, work, smem, st);  \
-      else launch_fast_variant<RN_CLS_BALANCED_BCE, false, BF>(segs, fp, select, work, smem, st);      \
-      break;                                                                                           \
-    default:                                                                                           \
-      launch_fast_variant<RN_CLS_NONE, true, BF>(segs, fp, select, work, smem, st);                    \
-      break;                                                                                           \
-  }
-  if (fp.bf16) {   // bf16x8 units (two float4 halves per 128-bit access)
-    RN_FAST_MODES(true)
-  } else {
-    RN_FAST_MODES(false)
-  }
-#undef RN_FAST_MODES
-  RN_CUDA_CHECK_LAUNCH("fast classification-loss kernel");
-  return RN_OK;
+  (void)units;
+  TileParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.logits = fp.logits;
+  tp.label = fp.label;
+  tp.dlogits = fp.dlogits;
+  tp.alpha = fp.alpha;
+  tp.eps = fp.eps;
+  tp.stats = fp.stats;
+  tp.stats_out = fp.stats_out;
+  tp.workspace = fp.ticket;
+  tp.num_classes = fp.num_classes;
+  tp.bf16 = fp.bf16;
+  tp.write_grad = fp.write_grad;
+  tp.sel_trigger = fp.sel_trigger;
+  tp.sel_thr = fp.sel_thr;
+  tp.sel_images = fp.sel_images;
+  tp.sel_capacity = fp.sel_capacity;
+  tp.sel_anchor = fp.sel_anchor;
+  tp.sel_score = fp.sel_score;
+  tp.sel_class = fp.sel_class;
+  tp.sel_count = fp.sel_count;
+  tp.status = fp.status;
+  return launch_cls_tile(segs, tp, mode & ~RN_CLS_GENERIC_FLAG, select, st);
 }
 
 }  // namespace rn
@@ -1258,16 +875,8 @@ using namespace rn;
 
 extern "C" int rn_set_option(const char* name, int value) {
   RN_REQUIRE(name, RN_ERR_BAD_ARG, "rn_set_option: NULL name");
-  if (strcmp(name, "fast_focal") == 0) {
-    g_fast_kernels = value != 0;
-    return RN_OK;
-  }
   if (strcmp(name, "exchange_timeout_ms") == 0) {
     rn::set_exchange_timeout_ms(value);
-    return RN_OK;
-  }
-  if (strcmp(name, "tile_kernel") == 0) {
-    g_tile_kernel = value != 0;
     return RN_OK;
   }
   rn::set_error("rn_set_option: unknown option '%s'", name);
@@ -1304,7 +913,7 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   const bool vec4 = (num_classes % 4 == 0) && aligned16(logits, rows->num_segments) &&
                     (!dense_labels || aligned16(label, rows->num_segments));
   const int vec = bf16 ? 8 : (vec4 ? 4 : 1);
-  RN_REQUIRE(!bf16 || (!dense_labels && num_classes % 8 == 0 && aligned16(logits, rows->num_segments) && g_fast_kernels),
+  RN_REQUIRE(!bf16 || (!dense_labels && num_classes % 8 == 0 && aligned16(logits, rows->num_segments)),
              RN_ERR_UNSUPPORTED,
              "rn_cls_sums: bf16 logits need compact labels, num_classes %% 8 == 0 and 16-byte aligned maps");
   SumsParams prm;
@@ -1328,7 +937,7 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
   bool units32 = true;
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (unsigned)prm.cv + (1ull << 24) >= (1ull << 32)) units32 = false;
-  if (!dense_labels && (vec4 || bf16) && g_fast_kernels && units32 && prm.cv <= kLossThreads) {
+  if (!dense_labels && (vec4 || bf16) && units32 && prm.cv <= kLossThreads) {
     // six float4 loads in flight per thread at 4 resident CTAs per SM measured best (4: 0.90 ms, 6: 0.85 ms,
     // 8 with 3 CTAs: 0.95 ms, 8 with 2 CTAs: 1.24 ms at COCO batch 64): the kernel is bound by resident warps, not
     // by bytes in flight.  bf16x8 units carry twice the classes (and accumulators): four loads in flight.
@@ -1350,7 +959,7 @@ extern "C" int rn_cls_sums(const rn_rows_t* rows, int num_classes, const rn_maps
 #undef RN_SUMS_FLAT
   }
   RN_REQUIRE(!bf16, RN_ERR_UNSUPPORTED, "rn_cls_sums: bf16 logits: no launch configuration for this shape");
-  if (!dense_labels && vec4 && g_fast_kernels && rows32 && prm.cv <= 256) {
+  if (!dense_labels && vec4 && rows32 && prm.cv <= 256) {
     prm.ry = 256 / prm.cv > 0 ? 256 / prm.cv : 1;
     const int fthreads = prm.cv * prm.ry;
     const size_t fsmem = (size_t)prm.ry * 2 * num_classes * sizeof(double);
@@ -1397,8 +1006,9 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
              "rn_cls_loss_fwd_bwd: workspace too small");
   const int base = mode & 15;
   const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
-  RN_REQUIRE(base >= RN_CLS_NONE && base <= RN_CLS_BALANCED_BCE && (mode & ~(15 | RN_CLS_DICE_FLAG)) == 0,
+  RN_REQUIRE(base >= RN_CLS_NONE && base <= RN_CLS_BALANCED_BCE && (mode & ~(15 | RN_CLS_DICE_FLAG | RN_CLS_GENERIC_FLAG)) == 0,
              RN_ERR_BAD_ARG, "rn_cls_loss_fwd_bwd: unknown mode %d", mode);
+  const bool generic = (mode & RN_CLS_GENERIC_FLAG) != 0;
   RN_REQUIRE(base != RN_CLS_NONE || dice, RN_ERR_BAD_ARG, "rn_cls_loss_fwd_bwd: empty mode");
   const Segs segs = make_segs(rows);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1432,9 +1042,9 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
   bool fits32 = true;  // the fast kernel indexes float4 units with 32-bit integers
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4 > 0 ? num_classes / 4 : 1) + (1ull << 24) >= (1ull << 32)) fits32 = false;
-  const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && g_fast_kernels && fits32 &&
+  const bool fast_ok = (base != RN_CLS_FOCAL || focus == 2.0f) && !dense && vec4 && !generic && fits32 &&
                        num_classes <= 2048;
-  if (dense && !bf16 && vec4 && g_fast_kernels && g_tile_kernel && (base != RN_CLS_FOCAL || focus == 2.0f) &&
+  if (dense && !bf16 && vec4 && !generic && (base != RN_CLS_FOCAL || focus == 2.0f) &&
       cls_tile_supported(num_classes, false, true)) {
     // dense float labels [rows, C] (the reference's own loss signatures, losses.py:115-141): the streaming
     // kernel with a second tile of labels per stage
@@ -1498,7 +1108,7 @@ extern "C" int rn_cls_loss_fwd_bwd(const rn_rows_t* rows, int num_classes, const
 extern "C" int rn_fused_select_supported(int num_classes, int mode, float focus, const rn_rows_t* rows) {
   const int base = mode & 15;
   if (!rows || num_classes % 4 != 0 || num_classes > 2048 || (base == RN_CLS_FOCAL && focus != 2.0f) ||
-      (base == RN_CLS_NONE && !(mode & RN_CLS_DICE_FLAG)) || !g_fast_kernels)
+      (base == RN_CLS_NONE && !(mode & RN_CLS_DICE_FLAG)) || (mode & RN_CLS_GENERIC_FLAG))
     return 0;
   for (int i = 0; i < rows->num_segments; ++i)
     if ((unsigned long long)rows->rows[i] * (num_classes / 4) + (1ull << 24) >= (1ull << 32)) return 0;
@@ -1590,7 +1200,7 @@ extern "C" int rn_head_loss(const rn_rows_t* rows, int num_classes, const rn_map
              "rn_head_loss: loss workspace too small");
   const int base = mode & 15;
   const bool dice = (mode & RN_CLS_DICE_FLAG) != 0;
-  RN_REQUIRE(base >= RN_CLS_NONE && base <= RN_CLS_BALANCED_BCE && (mode & ~(15 | RN_CLS_DICE_FLAG)) == 0 &&
+  RN_REQUIRE(base >= RN_CLS_NONE && base <= RN_CLS_BALANCED_BCE && (mode & ~(15 | RN_CLS_DICE_FLAG | RN_CLS_GENERIC_FLAG)) == 0 &&
                  (base != RN_CLS_NONE || dice),
              RN_ERR_BAD_ARG, "rn_head_loss: unknown mode %d", mode);
   RN_REQUIRE(logits_dtype == RN_DTYPE_F32 || logits_dtype == RN_DTYPE_BF16, RN_ERR_BAD_ARG, "unknown logits_dtype");
@@ -1600,7 +1210,7 @@ extern "C" int rn_head_loss(const rn_rows_t* rows, int num_classes, const rn_map
   const bool aligned = aligned16(logits, rows->num_segments) && (!grad || aligned16(dlogits, rows->num_segments)) &&
                        aligned16(reg_pred, rows->num_segments) && aligned16(reg_target, rows->num_segments) &&
                        (!maps_present(dreg) || aligned16(dreg, rows->num_segments));
-  const bool tile_ok = g_fast_kernels && g_tile_kernel && aligned && (base != RN_CLS_FOCAL || focus == 2.0f) &&
+  const bool tile_ok = !(mode & RN_CLS_GENERIC_FLAG) && aligned && (base != RN_CLS_FOCAL || focus == 2.0f) &&
                        cls_tile_supported(num_classes, bf16, false);
   if (!tile_ok) {   // separate launches (generic kernels); the fused selection needs the tile kernel
     RN_REQUIRE(!select, RN_ERR_UNSUPPORTED,

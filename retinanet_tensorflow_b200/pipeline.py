@@ -59,7 +59,8 @@ class DenseHeadPath(object):
     def __init__(self, image_size, num_classes, batch, max_gt, levels=None, *, cls_mode='focal',
                  anchor_size_mode='tf1_int_trunc', neg_iou=0.4, pos_iou=0.5, focus=2.0, alpha=0.25, eps=1e-7,
                  score_thr=0.5, nms_iou=0.5, max_output_per_class=1000, topk_per_level=0, capacity=4096,
-                 out_capacity=None, keep_iou=False, device=None, process_group=None, exchange='auto'):
+                 out_capacity=None, keep_iou=False, device=None, process_group=None, exchange='auto',
+                 generic_kernels=False):
         self.device = _lib.require_cuda(device)
         self.levels = build_levels() if levels is None else levels
         self.names = list(self.levels)
@@ -70,7 +71,9 @@ class DenseHeadPath(object):
         if cls_mode not in CLS_MODES:
             raise ValueError('cls_mode must be one of %s' % sorted(CLS_MODES))
         self.cls_mode = cls_mode
-        self.mode = CLS_MODES[cls_mode]
+        # generic_kernels=True: this path object takes the generic loss kernel (libm, IEEE division) even where the
+        # streaming kernel applies -- a per-object choice (RN_CLS_GENERIC_FLAG per call), used by the parity tests
+        self.mode = CLS_MODES[cls_mode] | (_lib.RN_CLS_GENERIC_FLAG if generic_kernels else 0)
         self.neg_iou, self.pos_iou = float(neg_iou), float(pos_iou)
         self.focus, self.alpha, self.eps = float(focus), float(alpha), float(eps)
         self.score_thr, self.nms_iou = float(score_thr), float(nms_iou)

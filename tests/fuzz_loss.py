@@ -61,6 +61,7 @@ def run_case(case):
     from retinanet_tensorflow_b200.pipeline import CLS_MODES
     c, seg_rows, lab, mode = case['c'], case['seg_rows'], case['lab'], case['mode']
     mode_bits = CLS_MODES[mode]
+    run_bits = mode_bits | (_lib.RN_CLS_GENERIC_FLAG if case['generic'] else 0)   # per-call kernel choice
     dev = torch.device('cuda')
     x = torch.from_numpy(case['x']).to(dev)
     if case['bf16']:
@@ -87,25 +88,21 @@ def run_case(case):
     hws = torch.zeros((_lib.lib.rn_loss_workspace_bytes(1),), dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr()
     dt = _lib.RN_DTYPE_BF16 if case['bf16'] else _lib.RN_DTYPE_F32
-    _lib.call('rn_set_option', b'fast_focal', 0 if case['generic'] else 1)
-    try:
-        _lib.call('rn_label_stats', C.byref(rows), c, C.byref(m_lab), _lib.ptr(stats), st)
-        if mode_bits & _lib.RN_CLS_DICE_FLAG:
-            _lib.call('rn_cls_sums', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, dt, _lib.ptr(stats),
-                      _lib.ptr(ws), ws_bytes, st)
-        if case['head']:
-            _lib.call('rn_head_loss', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), mode_bits, 2.0, 0.25, 1e-7,
-                      C.byref(m_dx), dt, C.byref(m_pred), C.byref(m_tgt), C.byref(m_dreg), _lib.ptr(stats), None,
-                      _lib.ptr(ws), ws_bytes, _lib.ptr(out), 0.0, 0, None, None, None, 0, st)
-        else:
-            _lib.call('rn_cls_loss_fwd_bwd', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, mode_bits, 2.0, 0.25,
-                      1e-7, C.byref(m_dx), dt, _lib.ptr(stats), _lib.ptr(ws), ws_bytes, st)
-            _lib.call('rn_huber_fwd_bwd', C.byref(rows), C.byref(m_pred), C.byref(m_tgt), C.byref(m_lab),
-                      C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(stats), _lib.ptr(hws), hws.numel(), st)
-            _lib.call('rn_loss_finalize', c, mode_bits, _lib.ptr(stats), _lib.ptr(out), st)
-        torch.cuda.synchronize()
-    finally:
-        _lib.call('rn_set_option', b'fast_focal', 1)
+    _lib.call('rn_label_stats', C.byref(rows), c, C.byref(m_lab), _lib.ptr(stats), st)
+    if mode_bits & _lib.RN_CLS_DICE_FLAG:
+        _lib.call('rn_cls_sums', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, dt, _lib.ptr(stats),
+                  _lib.ptr(ws), ws_bytes, st)
+    if case['head']:
+        _lib.call('rn_head_loss', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), run_bits, 2.0, 0.25, 1e-7,
+                  C.byref(m_dx), dt, C.byref(m_pred), C.byref(m_tgt), C.byref(m_dreg), _lib.ptr(stats), None,
+                  _lib.ptr(ws), ws_bytes, _lib.ptr(out), 0.0, 0, None, None, None, 0, st)
+    else:
+        _lib.call('rn_cls_loss_fwd_bwd', C.byref(rows), c, C.byref(m_x), C.byref(m_lab), 0, run_bits, 2.0, 0.25,
+                  1e-7, C.byref(m_dx), dt, _lib.ptr(stats), _lib.ptr(ws), ws_bytes, st)
+        _lib.call('rn_huber_fwd_bwd', C.byref(rows), C.byref(m_pred), C.byref(m_tgt), C.byref(m_lab),
+                  C.byref(_lib.Maps()), C.byref(m_dreg), _lib.ptr(stats), _lib.ptr(hws), hws.numel(), st)
+        _lib.call('rn_loss_finalize', c, mode_bits, _lib.ptr(stats), _lib.ptr(out), st)
+    torch.cuda.synchronize()
     got = out.cpu().numpy()
 
     mask = lab != -2

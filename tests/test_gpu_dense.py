@@ -72,19 +72,16 @@ def _run_dense(z, x, mode_bits, tile):
     out = torch.zeros((4,), dtype=torch.float32, device='cuda')
     seg = _lib.rows_of([rows])
     st = _lib.stream_ptr()
-    _lib.call('rn_set_option', b'tile_kernel', 1 if tile else 0)
-    try:
-        _lib.call('rn_label_stats_dense', rows, c, _lib.ptr(zd), _lib.ptr(stats), st)
-        if mode_bits & _lib.RN_CLS_DICE_FLAG:
-            _lib.call('rn_cls_sums', C.byref(seg), c, C.byref(_lib.maps_of([xd])), C.byref(_lib.maps_of([zd])), 1,
-                      _lib.RN_DTYPE_F32, _lib.ptr(stats), _lib.ptr(ws), nb, st)
-        _lib.call('rn_cls_loss_fwd_bwd', C.byref(seg), c, C.byref(_lib.maps_of([xd])), C.byref(_lib.maps_of([zd])), 1,
-                  mode_bits, 2.0, 0.25, 1e-7, C.byref(_lib.maps_of([g])), _lib.RN_DTYPE_F32, _lib.ptr(stats), _lib.ptr(ws),
-                  nb, st)
-        _lib.call('rn_loss_finalize', c, mode_bits, _lib.ptr(stats), _lib.ptr(out), st)
-        torch.cuda.synchronize()
-    finally:
-        _lib.call('rn_set_option', b'tile_kernel', 1)
+    run_bits = mode_bits | (0 if tile else _lib.RN_CLS_GENERIC_FLAG)   # per-call kernel choice
+    _lib.call('rn_label_stats_dense', rows, c, _lib.ptr(zd), _lib.ptr(stats), st)
+    if mode_bits & _lib.RN_CLS_DICE_FLAG:
+        _lib.call('rn_cls_sums', C.byref(seg), c, C.byref(_lib.maps_of([xd])), C.byref(_lib.maps_of([zd])), 1,
+                  _lib.RN_DTYPE_F32, _lib.ptr(stats), _lib.ptr(ws), nb, st)
+    _lib.call('rn_cls_loss_fwd_bwd', C.byref(seg), c, C.byref(_lib.maps_of([xd])), C.byref(_lib.maps_of([zd])), 1,
+              run_bits, 2.0, 0.25, 1e-7, C.byref(_lib.maps_of([g])), _lib.RN_DTYPE_F32, _lib.ptr(stats), _lib.ptr(ws),
+              nb, st)
+    _lib.call('rn_loss_finalize', c, mode_bits, _lib.ptr(stats), _lib.ptr(out), st)
+    torch.cuda.synchronize()
     return out.cpu().numpy(), g.cpu().numpy()
 
 

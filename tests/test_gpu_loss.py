@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 MODES = ['focal', 'bce_dice', 'bce', 'balanced_bce', 'balanced_bce_dice', 'focal_dice']
 
 
-def _setup(name, batch, mode):
+def _setup(name, batch, mode, generic=False):
     import torch
     from retinanet_tensorflow_b200 import synthetic
     from retinanet_tensorflow_b200.pipeline import DenseHeadPath
@@ -27,18 +27,15 @@ def _setup(name, batch, mode):
     logits, regs = synthetic.head_outputs(lab, reg, wl.num_classes, seed=7 + wl.config, device='cpu')
     boxes, classes, counts = synthetic.gt_batch(wl, batch)
     path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, cls_mode=mode,
-                         process_group=False)
+                         process_group=False, generic_kernels=generic)
     path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
     return wl, path, cls, mask, reg, logits, regs
 
 
-@pytest.fixture(params=[1, 0], ids=['fast_focal', 'generic'])
+@pytest.fixture(params=[1, 0], ids=['streaming', 'generic'])
 def focal_kernel(request):
-    """Run focal cases through both the specialised and the generic kernel."""
-    from retinanet_tensorflow_b200 import _lib
-    _lib.call('rn_set_option', b'fast_focal', request.param)
-    yield request.param
-    _lib.call('rn_set_option', b'fast_focal', 1)
+    """Run focal cases through both the streaming and the generic kernel (a per-path choice, no global switch)."""
+    return request.param
 
 
 def _outside_pure_rtol(got, want, rtol=1e-5):
@@ -56,7 +53,7 @@ def test_fused_loss_matches_oracle(name, batch, mode, focal_kernel):
         pytest.skip('the generic kernel is what runs anyway')
     if name in ('coco', 'crowded') and mode not in ('focal', 'bce_dice'):
         pytest.skip('the headline shapes run the two modes the bench reports')
-    wl, path, cls, mask, reg, logits, regs = _setup(name, batch, mode)
+    wl, path, cls, mask, reg, logits, regs = _setup(name, batch, mode, generic=(focal_kernel == 0))
     out = path.loss(logits.cuda(), regs.cuda()).cpu().numpy()
     torch.cuda.synchronize()
     x, r = logits.numpy(), regs.numpy()
@@ -96,12 +93,12 @@ def test_fast_focal_extreme_logits_stay_finite_and_close():
     rg = regs.cuda()
     a = path.loss(lg, rg).clone()
     ga = path.dlogits.clone()
-    _lib.call('rn_set_option', b'fast_focal', 0)
+    path.mode |= _lib.RN_CLS_GENERIC_FLAG
     try:
         b = path.loss(lg, rg).clone()
         gb = path.dlogits.clone()
     finally:
-        _lib.call('rn_set_option', b'fast_focal', 1)
+        path.mode &= ~_lib.RN_CLS_GENERIC_FLAG
     assert torch.isfinite(a).all() and torch.isfinite(ga).all()
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5)
     ga, gb, x = ga.cpu().numpy(), gb.cpu().numpy(), lg.cpu().numpy()
