@@ -300,6 +300,22 @@ RN_API int rn_mask_scan(const rn_rows_t* rows, const rn_maps_t* mask, void* d_wo
 RN_API int rn_mask_gather(const rn_rows_t* rows, int row_bytes, const rn_maps_t* src, const rn_maps_t* mask,
                           const void* d_workspace, void* d_out, void* stream);
 
+/* ---- the two ends of the path on the device --------------------------------------- */
+/* data_loaders/shapes.py:26-53,113-131: rasterise the synthetic Shapes images into an image batch
+ * d_image [B, H, W, 3] u8 (RGB as the reference's colour tuples): background colour d_background [B, 3], then
+ * d_counts[b] shapes in list order (later ones paint over earlier ones).  d_specs [B, max_shapes, 8] int32 =
+ * (kind, x, y, s, r, g, b, 0), kind 0 square / 1 triangle / 2 circle (the reference's class order).  Squares and
+ * circles match cv2.rectangle / cv2.circle pixel for pixel; triangles match cv2.fillPoly up to isolated edge pixels. */
+RN_API int rn_shapes_render(int batch, int height, int width, int max_shapes, const int32_t* d_specs,
+                            const int32_t* d_counts, const uint8_t* d_background, uint8_t* d_image, void* stream);
+
+/* utils.draw_bounding_boxes (utils.py:120-148) on the device detection lists: 1-pixel outlines of
+ * d_boxes [B, capacity, 4] (normalised [ymin, xmin, ymax, xmax]; pixel = round(box * [H, W, H, W])) in the colour
+ * d_palette [num_classes, 3] of d_classes, for the first d_counts[b] entries of every image.  No text labels. */
+RN_API int rn_draw_boxes(int batch, int height, int width, int capacity, const float* d_boxes,
+                         const int32_t* d_classes, const int32_t* d_counts, const uint8_t* d_palette,
+                         int num_classes, uint8_t* d_image, void* stream);
+
 /* ---- multi-GPU exchange over NVLink peer memory -------------------------------------------- */
 /* All-reduce(sum) of d_stats[offset : offset + len) across `world` ranks WITHOUT a collective
  * library: every rank owns a mailbox of rn_stats_mailbox_bytes() in peer-mapped memory (zeroed

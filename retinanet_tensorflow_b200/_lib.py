@@ -108,6 +108,8 @@ PROTOTYPES = {
     'rn_mask_workspace_bytes': (_sz, [_RP]),
     'rn_mask_scan': (_i, [_RP, _MP, _vp, _sz, _vp, _vp]),
     'rn_mask_gather': (_i, [_RP, _i, _MP, _MP, _vp, _vp, _vp]),
+    'rn_shapes_render': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'rn_draw_boxes': (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     'rn_stats_mailbox_bytes': (_sz, [_i, _i, _i]),
     'rn_stats_exchange': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, C.c_uint64, _vp, _vp]),
     'rn_stats_exchange_auto': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),

@@ -154,9 +154,32 @@ def oracle_case():
     np.savez_compressed(os.path.join(HERE, 'oracle_shapes_case.npz'), **out)
 
 
+def reference_shapes_images():
+    """reference_shapes_images.npz: six 200x200 images drawn by the REAL data_loaders/shapes.py (random_image +
+    draw_shape with OpenCV), with their specifications -- what rn_shapes_render has to reproduce."""
+    sys.path.insert(0, REF)
+    from data_loaders import shapes as ref_shapes
+    out = {}
+    for seed in range(6):
+        random.seed(100 + seed)
+        size = (200, 200)
+        bg, shp = ref_shapes.random_image(size)
+        image = np.ones([*size, 3], np.uint8) * np.array(bg).reshape(1, 1, 3).astype(np.uint8)
+        for shape, color, dims in shp:
+            image = ref_shapes.draw_shape(image, shape, dims, color)
+        out['image_%d' % seed] = image
+        out['bg_%d' % seed] = np.array(bg)
+        out['n_%d' % seed] = np.int32(len(shp))
+        out['kinds_%d' % seed] = np.array([['square', 'triangle', 'circle'].index(s[0]) for s in shp], np.int32)
+        out['colors_%d' % seed] = np.array([s[1] for s in shp], np.int32).reshape(-1, 3)
+        out['dims_%d' % seed] = np.array([s[2] for s in shp], np.int32).reshape(-1, 3)
+    np.savez_compressed(os.path.join(HERE, 'reference_shapes_images.npz'), **out)
+
+
 if __name__ == '__main__':
     reference_levels()
     reference_shapes()
+    reference_shapes_images()
     reference_tests()
     oracle_case()
     for f in sorted(os.listdir(HERE)):

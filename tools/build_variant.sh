@@ -6,7 +6,7 @@ ROOT=$(cd $(dirname $0)/.. && pwd)
 OUT=$ROOT/retinanet_tensorflow_b200/lib/variants
 mkdir -p $OUT/$1
 cd $ROOT/retinanet_tensorflow_b200/csrc
-for f in rn_api rn_assign rn_loss rn_loss_tile rn_decode rn_compact rn_exchange; do
+for f in rn_api rn_assign rn_loss rn_loss_tile rn_decode rn_compact rn_shapes rn_exchange; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden \
     -I$ROOT/include --expt-relaxed-constexpr $2 -c $f.cu -o $OUT/$1/$f.o &
 done
