@@ -1,23 +1,19 @@
-// K2/K3: fused classification loss (focal | BCE | balanced BCE, +dice) and Huber regression loss,
-// forward and backward in one pass over the logits (losses.py:6-15,50-60,96-110,115-152;
-// utils.process_labels_and_logits' sigmoid and trainable masking, utils.py:249,270).
+// K2/K3 entry points (classification + regression losses, forward and backward: losses.py:6-15,50-60,96-110,
+// 115-152; utils.process_labels_and_logits' sigmoid and trainable masking, utils.py:249,270) and the kernels that are
+// NOT the product's streaming kernel.
 //
-// The kernels stream `[rows, C]` logits once (128-bit loads), take the per-row compact label
-// (class | background | ignored) written by K1, and write d(loss)/d(logits) with the global
-// normalisers already applied.  Normalisers (M, num_fg, per-class sums) live in a small
-// double-precision stats vector in device memory so that nothing is synchronised with the host
-// and the multi-GPU exchange is one all-reduce of that vector.  Loss sums are reduced
-// warp -> block -> (per-block partials, fixed-order final pass by the last block), so results
-// are run-to-run deterministic.
+// Normalisers (M, num_fg, per-class sums) live in a small double-precision stats vector in device memory, so nothing
+// is synchronised with the host and the multi-GPU exchange is one all-reduce of that vector.
 //
-// Layout of this file:
-//   cls_loss_kernel       generic kernel (any mode, dense or compact labels, any C, any focus):
-//                         libm + IEEE division, ~110 instructions per logit -- the fallback
-//   cls_fast_kernel       the product path for compact labels and C % 4 == 0 (focal with focus 2,
-//                         BCE, balanced BCE, +-dice, float32 or bf16x8): ~34 instructions per logit,
-//                         optional fused candidate pre-selection (rn_cls_loss_select)
-//   cls_sums_*            dice phase 1 (per-class sums), huber_*, loss_finalize, elementwise /
-//                         column-sum / softmax forms for the reference's own signatures
+// Layout:
+//   rn_loss_tile.cu       (other file) cls_tile_kernel -- the product path: TMA-bulk ring, dynamic tiles, packed
+//                         f32x2 math, careful queue; compact or dense labels, float32 or bf16, +-dice, fused Huber /
+//                         candidate pre-selection / final scalars.  The entry points below route to it.
+//   cls_loss_kernel       generic kernel (any mode, dense or compact labels, any C, any focus): libm + IEEE division,
+//                         ~110 instructions per logit -- the fallback for C % 4 != 0 / focus != 2 and, with
+//                         RN_CLS_GENERIC_FLAG, the parity tests' second implementation
+//   cls_sums_*            dice phase 1 (per-class sums); huber_*; loss_finalize; elementwise / column-sum / softmax
+//                         forms for the reference's own signatures
 #include <string.h>
 
 #include <cmath>

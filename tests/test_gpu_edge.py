@@ -268,3 +268,69 @@ def test_denormal_and_zero_sized_ground_truth_boxes():
             assert np.array_equal(np.isneginf(got), np.isneginf(want))
             fin = np.isfinite(want)
             helpers.assert_close(got[fin], want[fin], rtol=1e-5, atol=1e-7, what='deltas ' + pn)
+
+
+def test_prefetched_assignment_equals_inline_steps():
+    """DenseHeadPath.prefetch_assign (the next step's K1 + statistics on their own stream, into the other label
+    set) must reproduce a plain sequence of steps whose ground truth CHANGES from step to step."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['voc']
+    B = 4
+    gts = [[torch.from_numpy(x).cuda() for x in synthetic.gt_batch(wl, B, first_image=f)] for f in (0, 10, 20, 30)]
+    ref = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, B, wl.max_gt, process_group=False, capacity=8192)
+    ref.assign(*gts[0])
+    logits, regs = synthetic.head_outputs(ref.label, ref.deltas, wl.num_classes, seed=3, device='cuda')
+    want = []
+    for g in gts:
+        ref.step(*g, logits, regs)
+        torch.cuda.synchronize()
+        want.append((ref.loss_out.clone(), ref.det_count.clone(), ref.dlogits.clone(), ref.label.clone()))
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, B, wl.max_gt, process_group=False, capacity=8192)
+    path.prefetch_assign(*gts[0])
+    for i, g in enumerate(gts):
+        path.step(*g, logits, regs, overlap_detect=True)
+        if i + 1 < len(gts):
+            path.prefetch_assign(*gts[i + 1])
+        path.join()
+        torch.cuda.synchronize()
+        assert torch.equal(path.label, want[i][3]), 'labels of step %d' % i
+        assert torch.equal(path.loss_out, want[i][0]), (i, path.loss_out.tolist(), want[i][0].tolist())
+        assert torch.equal(path.det_count, want[i][1]) and torch.equal(path.dlogits, want[i][2])
+    path.check_status(ignore=12)
+
+
+def test_head_loss_equals_separate_launches():
+    """rn_head_loss (classification + Huber + final scalars in one launch) against rn_cls_loss_fwd_bwd +
+    rn_huber_fwd_bwd + rn_loss_finalize: same gradients bit for bit, same scalars (the Huber sum is accumulated in
+    fixed point in one and in double in the other: 1e-6)."""
+    import ctypes as C
+    import torch
+    from retinanet_tensorflow_b200 import _lib, synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['voc']
+    B = 3
+    gt = [torch.from_numpy(x).cuda() for x in synthetic.gt_batch(wl, B)]
+    for mode in ('focal', 'bce_dice', 'balanced_bce'):
+        path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, B, wl.max_gt, cls_mode=mode, process_group=False)
+        path.assign(*gt)
+        logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=5, device='cuda')
+        a = path.loss(logits, regs).clone()
+        ga, gra = path.dlogits.clone(), path.dreg.clone()
+        st = _lib.stream_ptr()
+        stats = path.stats.clone()
+        m_logits, _ = path._maps(logits, wl.num_classes, path._LOGIT_DTYPES)
+        m_reg, _ = path._maps(regs, 4)
+        gb, grb = torch.empty_like(ga), torch.empty_like(gra)
+        out = torch.zeros((4,), dtype=torch.float32, device='cuda')
+        ws = torch.zeros_like(path._loss_ws)
+        _lib.call('rn_cls_loss_fwd_bwd', C.byref(path.rows), wl.num_classes, C.byref(m_logits), C.byref(path._m_label), 0,
+                  path.mode, 2.0, 0.25, 1e-7, C.byref(path._merged_maps(gb, 4 * wl.num_classes)), _lib.RN_DTYPE_F32,
+                  _lib.ptr(stats), _lib.ptr(ws), ws.numel(), st)
+        _lib.call('rn_huber_fwd_bwd', C.byref(path.rows), C.byref(m_reg), C.byref(path._m_deltas), C.byref(path._m_label),
+                  C.byref(_lib.Maps()), C.byref(path._merged_maps(grb, 16)), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), st)
+        _lib.call('rn_loss_finalize', wl.num_classes, path.mode, _lib.ptr(stats), _lib.ptr(out), st)
+        torch.cuda.synchronize()
+        assert torch.equal(ga, gb) and torch.equal(gra, grb), mode
+        assert torch.allclose(a, out, rtol=1e-6, atol=0), (mode, a.tolist(), out.tolist())
