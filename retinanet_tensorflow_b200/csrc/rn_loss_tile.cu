@@ -116,14 +116,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-// this thread's earlier cp.async copies arrive on `bar` when they complete (no pending-count increment)
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-
 // ---- packed float32x2 math (Blackwell: two lanes of an FMA-pipe instruction) ----------------------------
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -453,21 +445,28 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
       const unsigned left = (unsigned)segs.rows[s] - row0;
       const unsigned nrows = left < prm.tile_rows ? left : prm.tile_rows;
       unsigned char* st = s_stage + (size_t)stage * prm.stage_bytes;
+      // the tile's compact labels: one more bulk copy when the 4-byte rows allow it (16-byte aligned source, whole
+      // 16-byte size -- every full tile of a 16-byte aligned level), else plain loads by the producer lanes
+      const int32_t* lab_g = DENSE ? nullptr : reinterpret_cast<const int32_t*>(prm.label.p[s]) + row0;
+      const bool lab_bulk = !DENSE && ((reinterpret_cast<uintptr_t>(lab_g) & 15u) == 0) && ((nrows & 3u) == 0);
       if (lane == 0) {
         tile_info[stage] = make_int4(s, (int)row0, (int)nrows, 0);
         const unsigned bytes = nrows * row_bytes;
-        mbar_expect_tx(full, DENSE ? 2 * bytes : bytes);
+        mbar_expect_tx(full, DENSE ? 2 * bytes : (lab_bulk ? bytes + nrows * 4u : bytes));
         bulk_g2s(smem_u32(st), reinterpret_cast<const unsigned char*>(prm.logits.p[s]) + (size_t)row0 * row_bytes, bytes,
                  full);
         if (DENSE)
           bulk_g2s(smem_u32(st + prm.x_bytes),
                    reinterpret_cast<const unsigned char*>(prm.label.p[s]) + (size_t)row0 * row_bytes, bytes, full);
+        else if (lab_bulk)
+          bulk_g2s(smem_u32(st + prm.x_bytes), lab_g, nrows * 4u, full);
       }
       if (!DENSE) {
-        const int32_t* lab_g = reinterpret_cast<const int32_t*>(prm.label.p[s]) + row0;
-        const uint32_t lab_s = smem_u32(st + prm.x_bytes);
-        for (unsigned r = lane; r < nrows; r += 32) cp_async4(lab_s + 4 * r, lab_g + r);
-        cp_async_arrive(full);
+        if (!lab_bulk) {
+          int32_t* lab_s = reinterpret_cast<int32_t*>(st + prm.x_bytes);
+          for (unsigned r = lane; r < nrows; r += 32) lab_s[r] = __ldg(lab_g + r);
+        }
+        mbar_arrive(full);   // one arrival per producer lane (release: orders the plain stores above)
       }
     }
   } else {

@@ -131,6 +131,10 @@ def run_case(case):
     scale = float(np.abs(g_ref[ok]).max()) if ok.any() else 0.0
     # focal, saturated logits (x > 9): the reference's own 1 - p is quantised (see test_gpu_loss.py)
     sat = (x_ref > 9.0) if 'focal' in mode else np.zeros_like(ok)
+    if 'dice' in mode:
+        # the dice gradient carries p (1 - p) (TF's SigmoidGrad y (1 - y)): for p -> 1 the float32 `1 - p` has few
+        # significant bits (x = 5.3: a 1-ulp change of p moves it by 1.2e-5 relative) on ANY implementation
+        sat = sat | (x_ref > 4.0)
     rtol = 2.0 ** -7 if case['bf16'] else 1e-5
     helpers.assert_close(np.where(sat | ~ok, 0, g), np.where(sat | ~ok, 0, g_ref), rtol=rtol, atol=1e-6 * scale + 1e-12,
                          what='dlogits')

@@ -69,6 +69,37 @@ def main():
     bx = np.concatenate([rng.uniform(0, .4, (6, 7, 9, 2)), rng.uniform(.5, 1, (6, 7, 9, 2))], -1).astype(np.float32)
     utils.nms_classwise(utils.boxes_decode(probs, bx), 4)
     utils.iou(bx, bx)
+    # round 2: dense labels through the streaming kernel (C % 4 == 0), trainable masking by the compaction kernels,
+    # an assignment launched one step ahead, the Shapes rasteriser and the box drawing
+    z8 = (rng.uniform(size=(700, 8)) > 0.97).astype(np.float32)
+    x8 = torch.tensor(rng.normal(-3, 2, (700, 8)).astype(np.float32), device='cuda', requires_grad=True)
+    (losses.classification_loss(z8, x8, z8.max(-1) > 0.5, mode='focal') +
+     losses.classification_loss(z8, x8, z8.max(-1) > 0.5, mode='bce_dice')).backward()
+    wl = synthetic.Workload('voc8', 2, 160, 192, 8, 20, 2)
+    boxes, cls, counts = synthetic.gt_batch(wl, 2)
+    gt = [torch.from_numpy(v).cuda() for v in (boxes, cls, counts)]
+    path = DenseHeadPath((wl.image_h, wl.image_w), 8, 2, wl.max_gt, capacity=512, process_group=False)
+    path.assign(*gt)
+    logits, regs = synthetic.head_outputs(path.label, path.deltas, 8, seed=4, device='cuda')
+    for _ in range(3):
+        path.step(*gt, logits, regs, overlap_detect=True)
+        path.prefetch_assign(*gt)
+    path.join()
+    levels = build_levels()
+    per = [dataset.build_labels([wl.image_h, wl.image_w], torch.from_numpy(cls[i, :counts[i]]),
+                                torch.from_numpy(boxes[i, :counts[i]]), levels, 8) for i in range(2)]
+    feats = {'image': torch.empty((2, wl.image_h, wl.image_w, 0), device='cuda'),
+             'detection': {'classifications': {k: torch.stack([p[0][k] for p in per]) for k in levels},
+                           'regressions': {k: torch.stack([p[1][k] for p in per]) for k in levels}},
+             'trainable_masks': {k: torch.stack([p[2][k] for p in per]) for k in levels}}
+    head = {'detection': {'classifications': path.per_level(logits, (8,)), 'regressions': path.per_level(regs, (4,))}}
+    lab, log = utils.process_labels_and_logits(feats, head, levels)
+    losses.loss(lab['detection_trainable'], log['detection_trainable'], mode='focal')
+    log['detection_trainable'].classification.prob
+    from retinanet_tensorflow_b200 import synthetic_shapes
+    data = synthetic_shapes.Shapes(image_size=(120, 160)).batch(3)
+    synthetic_shapes.draw_bounding_boxes(data['image'], data['gt_boxes'], data['gt_classes'].clamp(min=0), data['gt_counts'],
+                                         num_classes=3)
     torch.cuda.synchronize()
     print('SANITIZE_RUN_DONE')
 
