@@ -334,3 +334,41 @@ def test_head_loss_equals_separate_launches():
         torch.cuda.synchronize()
         assert torch.equal(ga, gb) and torch.equal(gra, grb), mode
         assert torch.allclose(a, out, rtol=1e-6, atol=0), (mode, a.tolist(), out.tolist())
+
+
+def test_assign_with_the_largest_supported_gt_capacity():
+    """max_gt = 2048 needs 90 KB of dynamic shared memory in the assign kernel (an opt-in above 48 KB): the launch must
+    succeed and give the same labels as a tight capacity."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    wl = synthetic.WORKLOADS['voc']
+    boxes, classes, counts = synthetic.gt_batch(wl, 2)
+    small = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 2, wl.max_gt, process_group=False)
+    small.assign(*(torch.from_numpy(x).cuda() for x in (boxes, classes, counts)))
+    big_n = 2048
+    bb = np.zeros((2, big_n, 4), np.float32)
+    cc = np.full((2, big_n), -1, np.int32)
+    bb[:, :wl.max_gt], cc[:, :wl.max_gt] = boxes, classes
+    big = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, 2, big_n, process_group=False)
+    big.assign(torch.from_numpy(bb).cuda(), torch.from_numpy(cc).cuda(), torch.from_numpy(counts).cuda())
+    torch.cuda.synchronize()
+    big.check_status()
+    assert torch.equal(big.label, small.label) and torch.equal(big.matched, small.matched)
+    assert torch.equal(big.deltas, small.deltas)
+
+
+def test_column_sum_losses_backward_twice():
+    """dice / jaccard / fixed-IoU keep only plain tensors for backward: a second backward (retain_graph) works and
+    gives the same gradient."""
+    import torch
+    from retinanet_tensorflow_b200 import losses
+    g = torch.Generator().manual_seed(0)
+    z = (torch.rand((300, 8), generator=g) > 0.9).float().cuda()
+    x = torch.randn((300, 8), generator=g).cuda().requires_grad_(True)
+    for fn in (lambda: losses.dice_loss(z, x, smooth=0., axis=0).mean(), lambda: losses.jaccard_loss(z, x, axis=0).mean(),
+               lambda: losses.fixed_iou_loss(z, x, axis=0, smooth=1e-7).mean()):
+        out = fn()
+        (g1,) = torch.autograd.grad(out, x, retain_graph=True)
+        (g2,) = torch.autograd.grad(out, x)
+        assert torch.equal(g1, g2) and torch.isfinite(g1).all() and g1.abs().sum() > 0
