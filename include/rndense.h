@@ -182,6 +182,17 @@ RN_API int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float* d_g
                             const rn_maps_t* matched, const rn_maps_t* label,
                             const rn_maps_t* deltas, const rn_maps_t* iou_max,
                             double* d_stats, uint32_t* d_status, void* stream);
+/* Same with an explicit work decomposition: one CTA handles patch_sy x patch_sx sub-patches of 8 x 8 cells and
+ * shares the per-image work (GT conversion + culling, encoding table) between them.  0, 0 = automatic (what
+ * rn_assign_encode uses: 2 x 2 for launches that fill the device, 1 x 1 otherwise).  The results do not depend on
+ * the decomposition; the parity tests run several. */
+RN_API int rn_assign_encode_patch(const rn_pyramid_t* pyr, int batch, const float* d_gt_boxes,
+                                  const int32_t* d_gt_classes, const int32_t* d_gt_counts, int max_gt,
+                                  int num_classes, float neg_iou_thr, float pos_iou_thr,
+                                  const rn_maps_t* matched, const rn_maps_t* label,
+                                  const rn_maps_t* deltas, const rn_maps_t* iou_max,
+                                  double* d_stats, uint32_t* d_status, int patch_sy, int patch_sx,
+                                  void* stream);
 
 /* Dense reference layout from compact labels: classification one-hot f32 [.., C] (zero rows
  * for background and ignored anchors, dataset.py:93-100) and trainable mask u8 [..]

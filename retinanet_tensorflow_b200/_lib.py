@@ -88,6 +88,7 @@ PROTOTYPES = {
     'rn_maps_from_merged': (_i, [_PP, _i, _vp, _sz, _MP]),
     'rn_anchor_generate': (_i, [_PP, _vp, _vp, _vp]),
     'rn_assign_encode': (_i, [_PP, _i, _vp, _vp, _vp, _i, _i, _f, _f, _MP, _MP, _MP, _MP, _vp, _vp, _vp]),
+    'rn_assign_encode_patch': (_i, [_PP, _i, _vp, _vp, _vp, _i, _i, _f, _f, _MP, _MP, _MP, _MP, _vp, _vp, _i, _i, _vp]),
     'rn_labels_dense': (_i, [_RP, _i, _MP, _MP, _MP, _vp]),
     'rn_flip_labels': (_i, [_PP, _i, _MP, _MP, _MP, _MP, _vp]),
     'rn_iou_pairwise': (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),

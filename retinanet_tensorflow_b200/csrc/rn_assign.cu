@@ -1,13 +1,17 @@
 // K1: anchor-vs-GT IoU matching + box-delta encoding (dataset.level_labels, dataset.py:43-123),
 // plus the small label-format kernels around it (dense one-hot, flip, pairwise IoU, label stats).
 //
-// One CTA owns a kTileH x kTileW patch of cells of one (image, level).  Anchors are regenerated
-// in registers (never read from memory); the image's GT boxes are converted corner -> centre ->
-// corner exactly as the reference does (dataset.py:48,74), culled against the patch's bounding
-// box (a GT that is disjoint from the patch has IoU == 0 with every anchor of it, so it can
-// neither win nor tie above 0) and staged in shared memory in their original order, which keeps
-// tf.argmax's first-maximum rule.  Each thread then scans the staged boxes for its anchors with
-// the reference's float32 op sequence (no FMA contraction, IEEE division).
+// One CTA owns a rectangular patch of cells of one (image, level): SY x SX sub-patches of kTileH x kTileW cells,
+// visited one after the other by the same threads (3 anchors per thread).  Everything that does not depend on the
+// anchor is done once per CTA: the image's GT boxes are converted corner -> centre -> corner exactly as the
+// reference does (dataset.py:48,74), culled against the patch's bounding box (a GT that is disjoint from the patch
+// has IoU == 0 with every anchor of it, so it can neither win nor tie above 0) and staged in shared memory in their
+// original order, which keeps tf.argmax's first-maximum rule; the log size ratios of the encoding
+// (dataset.py:110-112) depend only on (GT box, anchor shape), so they are tabulated once per CTA for the staged
+// boxes instead of being evaluated per anchor.  Anchors are regenerated in registers (never read from memory); each
+// thread scans the staged boxes for its anchors with the reference's float32 op sequence (no FMA contraction, IEEE
+// division).  Round 2 profile of the one-sub-patch form (profiles/r02_k1_breakdown.md): 1327 instructions per warp
+// of which only 27 % were the IoU scan -- 37 % were per-CTA fixed cost and 31 % the per-anchor encoding.
 #include "rn_common.cuh"
 #include "rn_tiles.cuh"
 
@@ -15,6 +19,14 @@ namespace rn {
 
 constexpr int kApt = 3;          // anchors per thread
 constexpr int kMaxGtSmem = 2048; // GT boxes per image the assign kernel can stage
+constexpr int kLutEntries = 576; // (staged GT + 1) x anchors-per-cell table of log size ratios (else: per anchor)
+
+#ifndef RN_ASSIGN_SUPER_Y
+#define RN_ASSIGN_SUPER_Y 2
+#endif
+#ifndef RN_ASSIGN_SUPER_X
+#define RN_ASSIGN_SUPER_X 2
+#endif
 
 struct AssignParams {
   const float4* gt_boxes;   // [B, max_gt]
@@ -27,33 +39,73 @@ struct AssignParams {
   double* stats;
   uint32_t* status;
   int tpc;  // threads per cell
+  // CTA patches: sy x sx sub-patches of kTileH x kTileW cells
+  int sy, sx;
+  int tiles_x[RN_MAX_LEVELS];     // CTA patches per grid row of the level
+  int tile_start[RN_MAX_LEVELS];  // first CTA patch of the level within one image
 };
 
-__global__ void __launch_bounds__(kTileH * kTileW * 6)
+// (log(t_h / a_h), log(t_w / a_w)), dataset.py:110-112.  The ratios keep the IEEE division: log() of a ratio near 1
+// turns a 2-ulp ratio error into an arbitrarily large RELATIVE error of a near-zero delta.  log_fast is for positive
+// normal finite arguments (sign 0, exponent field 1..254); anything else -- a zero-area, denormal-sized, negative or
+// non-finite box -- takes libm in one shared rare branch.
+__device__ __noinline__ float log_libm(float x) { return logf(x); }
 
+__device__ __forceinline__ float2 log_size_ratios(float th, float tw, float h, float w) {
+  const float rh = fdiv(th, h), rw = fdiv(tw, w);
+  float2 d = make_float2(log_fast(rh), log_fast(rw));
+  const bool nh = (unsigned)(__float_as_int(rh) - 0x00800000) < 0x7f000000u;
+  const bool nw = (unsigned)(__float_as_int(rw) - 0x00800000) < 0x7f000000u;
+  if (!(nh && nw)) {
+    if (!nh) d.x = log_libm(rh);
+    if (!nw) d.y = log_libm(rw);
+  }
+  return d;
+}
+
+// (the per-anchor form, taken only when too many boxes touch the patch for the table: kept out of line so that the
+//  common path keeps its registers)
+__device__ __noinline__ float2 log_size_ratios_direct(float th, float tw, float h, float w) {
+  return log_size_ratios(th, tw, h, w);
+}
+
+// 64 registers (no spills): five 192-thread CTAs per SM.  The compiler's own choice (80) leaves four and is 8 % slower,
+// 56 spills into the scan loop (profiles/r02_k1_breakdown.md).
+#ifndef RN_ASSIGN_MAXREG
+#define RN_ASSIGN_MAXREG 64
+#endif
+#define RN_ASSIGN_REGS __maxnreg__(RN_ASSIGN_MAXREG)
+
+__global__ void RN_ASSIGN_REGS
 assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ AssignParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_box = reinterpret_cast<float4*>(smem_raw);                       // [max_gt] recomputed corners
-  float4* s_ctr = s_box + prm.max_gt;                                        // [max_gt] (cy, cx, h, w) of the raw box
-  float* s_area = reinterpret_cast<float*>(s_ctr + prm.max_gt);              // [max_gt]
-  int* s_idx = reinterpret_cast<int*>(s_area + prm.max_gt);                  // [max_gt] original index
-  int* s_cls = s_idx + prm.max_gt;                                           // [max_gt] class id
+  // slot 0 is GT 0 (the match of anchors that overlap nothing, dataset.py:76), slots 1.. the staged boxes
+  const int slots = prm.max_gt + 1;
+  float4* s_box = reinterpret_cast<float4*>(smem_raw);                       // [slots] recomputed corners
+  float4* s_ctr = s_box + slots;                                             // [slots] (cy, cx, h, w) of the raw box
+  float* s_area = reinterpret_cast<float*>(s_ctr + slots);                   // [slots]
+  int* s_idx = reinterpret_cast<int*>(s_area + slots);                       // [slots] original index
+  int* s_cls = s_idx + slots;                                                // [slots] class id
+  __shared__ float2 s_lut[kLutEntries];
+  __shared__ float4 s_shape[RN_MAX_ANCHORS];   // per anchor shape: (h / 2, w / 2, 1 / h, 1 / w)
   __shared__ int s_warp_cnt[32];
-  __shared__ float4 s_ctr0;   // GT 0 (the match of anchors that overlap nothing, dataset.py:76)
-  __shared__ int s_cls0;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / pyr.tiles_per_image;
-  const int tile = blockIdx.x - b * pyr.tiles_per_image;
+  // grid: x = image, y = patch, coarse levels first -- their patches see most of the image's boxes and take longest,
+  // so they start first and the many light fine-level patches fill the end of the launch
+  const int b = blockIdx.x;
+  const int tile = gridDim.y - 1 - blockIdx.y;
   int l = 0;
-  for (int k = 1; k < pyr.num_levels; ++k) l += (tile >= pyr.level[k].tile_start) ? 1 : 0;
+  for (int k = 1; k < pyr.num_levels; ++k) l += (tile >= prm.tile_start[k]) ? 1 : 0;
   const rn_level_t& L = pyr.level[l];
-  const int t_local = tile - L.tile_start;
-  const int ty0 = (t_local / L.tiles_x) * kTileH;
-  const int tx0 = (t_local % L.tiles_x) * kTileW;
-  const int ty1 = min(ty0 + kTileH, L.grid_h) - 1;  // inclusive
-  const int tx1 = min(tx0 + kTileW, L.grid_w) - 1;
+  const int t_local = tile - prm.tile_start[l];
+  const int py = t_local / prm.tiles_x[l];
+  const int ty0 = py * (kTileH * prm.sy);
+  const int tx0 = (t_local - py * prm.tiles_x[l]) * (kTileW * prm.sx);
+  const int ty1 = min(ty0 + kTileH * prm.sy, L.grid_h) - 1;  // inclusive
+  const int tx1 = min(tx0 + kTileW * prm.sx, L.grid_w) - 1;
+  const int A = L.num_anchors;
 
   // ---- patch bounding box: fsub/fadd are monotone, so the extremes come from the corner cells
   // and the level's largest half sizes (precomputed on the host)
@@ -69,6 +121,12 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
   const int n_gt = min(max(__ldg(prm.gt_counts + b), 0), prm.max_gt);
   unsigned flags = 0;
   int n_kept = 0;
+  if (tid < A) {
+    const float h = L.anchor_h[tid], w = L.anchor_w[tid];
+    // the shifts take a reciprocal (rcp.approx + one Newton step, <= 1 ulp of the quotient); deltas are compared
+    // within 1e-5 relative, not bit-exactly
+    s_shape[tid] = make_float4(h * 0.5f, w * 0.5f, rcp_newton(h), rcp_newton(w));
+  }
   // (the first chunk is processed unconditionally so that its loads do not wait for the count)
   for (int base = 0; base < prm.max_gt && (base == 0 || base < n_gt); base += blockDim.x) {
     const int i = base + tid;
@@ -92,8 +150,9 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
           flags |= RN_FLAG_IOU_RANGE;
         keep = !(g.z < T0 || g.x > T2 || g.w < T1 || g.y > T3);
         if (i == 0) {
-          s_ctr0 = ctr;
-          s_cls0 = cls;
+          s_ctr[0] = ctr;
+          s_idx[0] = 0;
+          s_cls[0] = cls;
         }
       }
     }
@@ -108,7 +167,7 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
       tot += c;
     }
     if (keep) {
-      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      const int pos = 1 + off + __popc(m & ((1u << lane) - 1u));
       s_box[pos] = g;
       s_ctr[pos] = ctr;
       s_area[pos] = fmul(fsub(g.z, g.x), fsub(g.w, g.y));  // box_b_area (utils.py:84-85)
@@ -119,130 +178,149 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
     __syncthreads();
   }
 
-  // ---- this thread's anchors
+  // ---- log size ratios of every (staged box, anchor shape) pair, once per CTA
+  const bool use_lut = n_gt > 0 && (n_kept + 1) * A <= kLutEntries;   // CTA-uniform
+  if (use_lut) {
+    for (int e = tid; e < (n_kept + 1) * A; e += blockDim.x) {
+      const int j = e / A, a = e - j * A;
+      const float4 t = s_ctr[j];
+      s_lut[e] = log_size_ratios(t.z, t.w, L.anchor_h[a], L.anchor_w[a]);
+    }
+    __syncthreads();
+  }
+
+  // ---- this thread's anchor shapes (the same for every sub-patch)
   const int cell_local = tid / prm.tpc;
   const int sub = tid - cell_local * prm.tpc;
-  const int cy_i = ty0 + cell_local / kTileW;
-  const int cx_i = tx0 + cell_local % kTileW;
-  const bool cell_ok = cell_local < kTileH * kTileW && cy_i < L.grid_h && cx_i < L.grid_w;
-  const float cy = cell_centre(L.y0, L.y_step, cy_i);
-  const float cx = cell_centre(L.x0, L.x_step, cx_i);
+  const int cl_y = cell_local / kTileW, cl_x = cell_local % kTileW;
+  const int a_first = min(sub * kApt, A - 1);   // (threads past the last anchor shape recompute it and store nothing)
+  // cells of this warp within a sub-patch (warp-uniform): rows r_lo..r_hi, columns x_lo..x_hi
+  const int c_lo = (warp * 32) / prm.tpc, c_hi = min((warp * 32 + 31) / prm.tpc, kTileH * kTileW - 1);
+  const int r_lo = c_lo / kTileW, r_hi = c_hi / kTileW;
+  const int x_lo = r_lo == r_hi ? c_lo % kTileW : 0, x_hi = r_lo == r_hi ? c_hi % kTileW : kTileW - 1;
 
-  float a0[kApt], a1[kApt], a2[kApt], a3[kApt], aa[kApt], best[kApt];
-  int bestj[kApt];
-  bool ok[kApt];
-#pragma unroll
-  for (int k = 0; k < kApt; ++k) {
-    const int a = sub * kApt + k;
-    ok[k] = cell_ok && a < L.num_anchors;
-    const float h = L.anchor_h[min(a, RN_MAX_ANCHORS - 1)], w = L.anchor_w[min(a, RN_MAX_ANCHORS - 1)];
-    a0[k] = fsub(cy, h * 0.5f);  // from_center_box(anchor), dataset.py:74
-    a1[k] = fsub(cx, w * 0.5f);
-    a2[k] = fadd(cy, h * 0.5f);
-    a3[k] = fadd(cx, w * 0.5f);
-    aa[k] = fmul(fsub(a2[k], a0[k]), fsub(a3[k], a1[k]));  // box_a_area (utils.py:82-83)
-    best[k] = 0.f;
-    bestj[k] = -1;
-  }
+  int n_ign = 0, n_fg = 0;   // both rare: the common warp issues no atomic at all
+  if (n_gt == 0 && tid == 0) flags |= RN_FLAG_EMPTY_GT;
+  // (CTA-uniform) this image's rows of the level's maps
+  const long long img_row0 = (long long)b * L.grid_h * L.grid_w * A;
+  int32_t* const out_matched = reinterpret_cast<int32_t*>(prm.matched.p[l]) + img_row0;
+  int32_t* const out_label = reinterpret_cast<int32_t*>(prm.label.p[l]) + img_row0;
+  float4* const out_deltas = reinterpret_cast<float4*>(prm.deltas.p[l]) + img_row0;
+  float* const out_iou = prm.iou_max.p[0] ? reinterpret_cast<float*>(prm.iou_max.p[l]) + img_row0 : nullptr;
+  double* const npos = prm.stats ? prm.stats + RN_STAT_NPOS(0) : nullptr;
 
-  // ---- IoU scan (utils.iou, utils.py:70-92), strict '>' keeps the first maximum.  The IEEE
-  // division only runs when the pair can beat the running best: rcp.approx bounds the quotient
-  // to 4e-7 relative, so `approx * (1 + 2e-6) <= best` proves fl(inter / uni) <= best.
-  // Two cheap rejections before the per-anchor work (a rejected pair has IoU == 0, which can neither win nor
-  // tie above 0, so skipping it cannot change the arg-max or its first-maximum rule):
-  //   * per warp: the union of the warp's anchor boxes (shuffle-reduced once) against the GT -- uniform branch;
-  //   * per thread: the thread's three anchors are concentric (one aspect ratio, three scales), so a GT that
-  //     misses the hull of the three misses all of them.
-  float h0 = a0[0], h1 = a1[0], h2 = a2[0], h3 = a3[0];
+  // (warp-uniform loop bounds: sub-patches and warps that lie outside the grid have nothing to do; there is no CTA
+  //  barrier below)
+#pragma unroll 1
+  for (int sy0 = ty0; sy0 < ty0 + prm.sy * kTileH && sy0 + r_lo < L.grid_h; sy0 += kTileH) {
+#pragma unroll 1
+    for (int sx0 = tx0; sx0 < tx0 + prm.sx * kTileW && sx0 + x_lo < L.grid_w; sx0 += kTileW) {
+      const int cy_i = sy0 + cl_y, cx_i = sx0 + cl_x;
+      const bool cell_ok = cy_i < L.grid_h && cx_i < L.grid_w;
+      const float cy = cell_centre(L.y0, L.y_step, cy_i);
+      const float cx = cell_centre(L.x0, L.x_step, cx_i);
+
+      float a0[kApt], a1[kApt], a2[kApt], a3[kApt], aa[kApt], best[kApt];
+      int bestj[kApt];
 #pragma unroll
-  for (int k = 1; k < kApt; ++k) {
-    h0 = fminf(h0, a0[k]);
-    h1 = fminf(h1, a1[k]);
-    h2 = fmaxf(h2, a2[k]);
-    h3 = fmaxf(h3, a3[k]);
-  }
-  const float w0 = warp_min(h0), w1 = warp_min(h1), w2 = warp_max(h2), w3 = warp_max(h3);
-  for (int j = 0; j < n_kept; ++j) {
-    const float4 g = s_box[j];
-    if (g.z < w0 || g.x > w2 || g.w < w1 || g.y > w3) continue;   // misses every anchor of this warp
-    if (g.z < h0 || g.x > h2 || g.w < h1 || g.y > h3) continue;   // misses this thread's anchors
-    const float ga = s_area[j];
+      for (int k = 0; k < kApt; ++k) {
+        const float4 sh = s_shape[min(a_first + k, A - 1)];
+        a0[k] = fsub(cy, sh.x);  // from_center_box(anchor), dataset.py:74
+        a1[k] = fsub(cx, sh.y);
+        a2[k] = fadd(cy, sh.x);
+        a3[k] = fadd(cx, sh.y);
+        aa[k] = fmul(fsub(a2[k], a0[k]), fsub(a3[k], a1[k]));  // box_a_area (utils.py:82-83)
+        best[k] = 0.f;
+        bestj[k] = 0;   // slot 0 = GT 0: tf.argmax of an all-zero column
+      }
+
+      // ---- IoU scan (utils.iou, utils.py:70-92), strict '>' keeps the first maximum.
+      // Per warp, 32 staged boxes at a time are tested (one per lane) against the bounding box of the warp's cells
+      // grown by the level's largest half sizes; only the boxes that touch it are visited, in their original order.
+      // A skipped box has IoU == 0 with every anchor of the warp, which can neither win nor tie above 0, so the
+      // arg-max and its first-maximum rule are unchanged.  (Cells outside the grid compute along and store nothing.)
+      // The IEEE division only runs when the pair can beat the running best: fl(inter / uni) > best implies
+      // inter > best * uni, and the two products are compared with a 2e-6 margin (their roundings are 6e-8 each); a
+      // denormal-range intersection always takes the division.
+      const float w0 = fsub(cell_centre(L.y0, L.y_step, sy0 + r_lo), L.max_half_h);
+      const float w1 = fsub(cell_centre(L.x0, L.x_step, sx0 + x_lo), L.max_half_w);
+      const float w2 = fadd(cell_centre(L.y0, L.y_step, min(sy0 + r_hi, L.grid_h - 1)), L.max_half_h);
+      const float w3 = fadd(cell_centre(L.x0, L.x_step, min(sx0 + x_hi, L.grid_w - 1)), L.max_half_w);
+      for (int j0 = 1; j0 <= n_kept; j0 += 32) {
+        bool touches = false;
+        if (j0 + lane <= n_kept) {
+          const float4 g = s_box[j0 + lane];
+          touches = !(g.z < w0 || g.x > w2 || g.w < w1 || g.y > w3);
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, touches);
+        while (todo) {
+          const int j = j0 + __ffs(todo) - 1;
+          todo &= todo - 1;
+          const float4 g = s_box[j];
+          const float ga = s_area[j];
 #pragma unroll
-    for (int k = 0; k < kApt; ++k) {
-      const float yt = fmaxf(a0[k], g.x), xl = fmaxf(a1[k], g.y);
-      const float yb = fminf(a2[k], g.z), xr = fminf(a3[k], g.w);
-      if (!(yb < yt || xr < xl)) {
-        const float inter = fmul(fsub(yb, yt), fsub(xr, xl));
-        const float uni = fsub(fadd(aa[k], ga), inter);
-        const float approx = inter * rcp_approx(uni);
-        // (best == 0: always take the exact division -- a denormal intersection flushes `approx` to 0, but the
-        //  reference's argmax still prefers that tiny positive IoU over "no overlap")
-        if (approx * 1.000002f > best[k] || best[k] == 0.f) {
-          const float v = fdiv(inter, uni);
-          if (v > best[k]) {
-            best[k] = v;
-            bestj[k] = j;
+          for (int k = 0; k < kApt; ++k) {
+            const float yt = fmaxf(a0[k], g.x), xl = fmaxf(a1[k], g.y);
+            const float yb = fminf(a2[k], g.z), xr = fminf(a3[k], g.w);
+            if (!(yb < yt || xr < xl)) {
+              const float inter = fmul(fsub(yb, yt), fsub(xr, xl));
+              const float uni = fsub(fadd(aa[k], ga), inter);
+              if (inter * 1.000002f > best[k] * uni || inter < 1e-30f) {
+                const float v = fdiv(inter, uni);
+                if (v > best[k]) {
+                  best[k] = v;
+                  bestj[k] = j;
+                }
+              }
+            }
           }
+        }
+      }
+
+      // ---- labels + encoding for the matched box (all anchors, dataset.py:105-121)
+      const int row0 = (cy_i * L.grid_w + cx_i) * A + sub * kApt;
+#pragma unroll
+      for (int k = 0; k < kApt; ++k) {
+        const int a = sub * kApt + k;
+        if (cell_ok && a < A) {
+          int lab = RN_LABEL_BACKGROUND;
+          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+          int matched = -1;
+          if (n_gt > 0) {
+            const int j = bestj[k];
+            matched = s_idx[j];
+            const float4 t = s_ctr[j];   // (cy, cx, h, w) of the matched raw box
+            const bool pos = best[k] >= prm.pos_thr;                 // !bg_mask, dataset.py:83
+            const bool ign = !pos && !(best[k] < prm.neg_thr);       // !trainable_mask, dataset.py:87
+            if (pos) {
+              const int c = s_cls[j];
+              lab = (c >= 0 && c < prm.num_classes) ? c : RN_LABEL_BACKGROUND;  // one_hot of an out-of-range id is 0
+            } else if (ign) {
+              lab = RN_LABEL_IGNORE;
+            }
+            const float4 sh = s_shape[a];
+            d.x = fsub(t.x, cy) * sh.z;   // shifts, dataset.py:108
+            d.y = fsub(t.y, cx) * sh.w;
+            const float2 zw = use_lut ? s_lut[j * A + a] : log_size_ratios_direct(t.z, t.w, L.anchor_h[a], L.anchor_w[a]);
+            d.z = zw.x;                    // log(scales), dataset.py:110-112
+            d.w = zw.y;
+          }
+          out_matched[row0 + k] = matched;
+          out_label[row0 + k] = lab;
+          out_deltas[row0 + k] = d;
+          if (out_iou) out_iou[row0 + k] = best[k];
+          n_ign += lab == RN_LABEL_IGNORE;
+          n_fg += lab >= 0;
+          if (npos && lab >= 0) atomicAdd(npos + lab, 1.0);
         }
       }
     }
   }
 
-  // ---- labels + encoding for the matched box (all anchors, dataset.py:105-121)
-  int n_ign = 0, n_fg = 0;   // both rare: the common warp issues no atomic at all
-  if (n_gt == 0 && tid == 0) flags |= RN_FLAG_EMPTY_GT;
-  const long long cell_row = ((long long)b * L.grid_h * L.grid_w + (long long)cy_i * L.grid_w + cx_i) * L.num_anchors;
-#pragma unroll
-  for (int k = 0; k < kApt; ++k) {
-    if (!ok[k]) continue;
-    const int a = sub * kApt + k;
-    const long long row = cell_row + a;
-    int lab = RN_LABEL_BACKGROUND;
-    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-    int matched = -1;
-    if (n_gt > 0) {
-      const bool hit = bestj[k] >= 0;
-      matched = hit ? s_idx[bestj[k]] : 0;
-      const float4 t = hit ? s_ctr[bestj[k]] : s_ctr0;   // (cy, cx, h, w) of the matched raw box
-      const bool pos = best[k] >= prm.pos_thr;                 // !bg_mask, dataset.py:83
-      const bool ign = !pos && !(best[k] < prm.neg_thr);       // !trainable_mask, dataset.py:87
-      if (pos) {
-        const int c = hit ? s_cls[bestj[k]] : s_cls0;
-        lab = (c >= 0 && c < prm.num_classes) ? c : RN_LABEL_BACKGROUND;  // one_hot of an out-of-range id is 0
-      } else if (ign) {
-        lab = RN_LABEL_IGNORE;
-      }
-      // deltas are compared within 1e-5 relative, not bit-exactly.  The shifts take a reciprocal (rcp.approx + one
-      // Newton step, <= 1 ulp of the quotient); the scale ratios keep the IEEE division, because log() of a ratio
-      // near 1 turns a 2-ulp ratio error into an arbitrarily large RELATIVE error of a near-zero delta.
-      const float h = L.anchor_h[a], w = L.anchor_w[a];
-      d.x = fsub(t.x, cy) * rcp_newton(h);   // shifts, dataset.py:108
-      d.y = fsub(t.y, cx) * rcp_newton(w);
-      const float rh = fdiv(t.z, h), rw = fdiv(t.w, w);   // scales, dataset.py:110
-      d.z = log_fast(rh);                                 // log(scales), dataset.py:112
-      d.w = log_fast(rw);
-      // log_fast is for positive normal finite arguments (sign 0, exponent field 1..254); anything else -- a
-      // zero-area, denormal-sized, negative or non-finite box -- takes libm in one shared rare branch
-      const bool nh = (unsigned)(__float_as_int(rh) - 0x00800000) < 0x7f000000u;
-      const bool nw = (unsigned)(__float_as_int(rw) - 0x00800000) < 0x7f000000u;
-      if (!(nh && nw)) {
-        if (!nh) d.z = logf(rh);
-        if (!nw) d.w = logf(rw);
-      }
-    }
-    reinterpret_cast<int32_t*>(prm.matched.p[l])[row] = matched;
-    reinterpret_cast<int32_t*>(prm.label.p[l])[row] = lab;
-    reinterpret_cast<float4*>(prm.deltas.p[l])[row] = d;
-    if (prm.iou_max.p[0]) reinterpret_cast<float*>(prm.iou_max.p[l])[row] = best[k];
-    n_ign += lab == RN_LABEL_IGNORE;
-    n_fg += lab >= 0;
-    if (prm.stats && lab >= 0) atomicAdd(prm.stats + RN_STAT_NPOS(lab), 1.0);
-  }
-
   if (prm.stats) {
     // M = all anchors - ignored: the constant part is added once, ignored anchors are rare
-    if (blockIdx.x == 0 && tid == 0)
-      atomicAdd(prm.stats + RN_STAT_TRAINABLE, (double)pyr.anchors_per_image * (double)(gridDim.x / pyr.tiles_per_image));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+      atomicAdd(prm.stats + RN_STAT_TRAINABLE, (double)pyr.anchors_per_image * (double)gridDim.x);
     if (__any_sync(0xffffffffu, (n_ign | n_fg) != 0)) {
       n_ign = warp_sum(n_ign);
       n_fg = warp_sum(n_fg);
@@ -377,6 +455,17 @@ extern "C" int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float*
                                 int num_classes, float neg_iou_thr, float pos_iou_thr, const rn_maps_t* matched,
                                 const rn_maps_t* label, const rn_maps_t* deltas, const rn_maps_t* iou_max,
                                 double* d_stats, uint32_t* d_status, void* stream) {
+  return rn_assign_encode_patch(pyr, batch, d_gt_boxes, d_gt_classes, d_gt_counts, max_gt, num_classes, neg_iou_thr,
+                                pos_iou_thr, matched, label, deltas, iou_max, d_stats, d_status, 0, 0, stream);
+}
+
+extern "C" int rn_assign_encode_patch(const rn_pyramid_t* pyr, int batch, const float* d_gt_boxes,
+                                      const int32_t* d_gt_classes, const int32_t* d_gt_counts, int max_gt,
+                                      int num_classes, float neg_iou_thr, float pos_iou_thr, const rn_maps_t* matched,
+                                      const rn_maps_t* label, const rn_maps_t* deltas, const rn_maps_t* iou_max,
+                                      double* d_stats, uint32_t* d_status, int patch_sy, int patch_sx, void* stream) {
+  RN_REQUIRE(patch_sy >= 0 && patch_sy <= 64 && patch_sx >= 0 && patch_sx <= 64 && (patch_sy == 0) == (patch_sx == 0),
+             RN_ERR_BAD_ARG, "rn_assign_encode_patch: patch_sy / patch_sx must both be 0 (automatic) or in 1..64");
   RN_REQUIRE(pyr && d_gt_boxes && d_gt_classes && d_gt_counts, RN_ERR_BAD_ARG, "rn_assign_encode: NULL input");
   RN_REQUIRE(maps_present(matched) && maps_present(label) && maps_present(deltas), RN_ERR_BAD_ARG,
              "rn_assign_encode: matched, label and deltas maps are required");
@@ -407,10 +496,26 @@ extern "C" int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float*
   prm.status = d_status;
   prm.tpc = (na + kApt - 1) / kApt;
   const int threads = kTileH * kTileW * prm.tpc;
-  const size_t smem = (size_t)max_gt * (2 * sizeof(float4) + sizeof(float) + 2 * sizeof(int));
-  const long long blocks = (long long)batch * pyr->tiles_per_image;
-  RN_REQUIRE(blocks < (1ll << 31), RN_ERR_BAD_SHAPE, "too many tiles");
-  static size_t smem_opted = 48 * 1024;   // more than 48 KB of dynamic shared memory needs an opt-in (max_gt > ~1100)
+  // CTA patch = sy x sx sub-patches: the per-CTA work (GT staging, the log-ratio table) is shared by all of them.
+  // Small launches keep one sub-patch per CTA so that they still fill the device.
+  long long tiles8 = 0;
+  for (int l = 0; l < pyr->num_levels; ++l) tiles8 += (long long)pyr->level[l].tiles_x * pyr->level[l].tiles_y;
+  const bool big = tiles8 * batch >= (long long)num_sms() * 32;
+  prm.sy = patch_sy ? patch_sy : (big ? RN_ASSIGN_SUPER_Y : 1);
+  prm.sx = patch_sx ? patch_sx : (big ? RN_ASSIGN_SUPER_X : 1);
+  int tiles = 0;
+  for (int l = 0; l < RN_MAX_LEVELS; ++l) {
+    prm.tiles_x[l] = 1;
+    prm.tile_start[l] = tiles;
+    if (l < pyr->num_levels) {
+      const rn_level_t& L = pyr->level[l];
+      prm.tiles_x[l] = (L.grid_w + kTileW * prm.sx - 1) / (kTileW * prm.sx);
+      tiles += prm.tiles_x[l] * ((L.grid_h + kTileH * prm.sy - 1) / (kTileH * prm.sy));
+    }
+  }
+  const size_t smem = (size_t)(max_gt + 1) * (2 * sizeof(float4) + sizeof(float) + 2 * sizeof(int));
+  RN_REQUIRE(tiles <= 65535, RN_ERR_BAD_SHAPE, "rn_assign_encode: more than 65535 patches per image");
+  static size_t smem_opted = 44 * 1024;   // more than 48 KB of shared memory (static + dynamic) needs an opt-in (max_gt > ~1000)
   if (smem > smem_opted) {
     if (cudaFuncSetAttribute(assign_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
@@ -426,7 +531,7 @@ extern "C" int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float*
     cudaFuncSetAttribute(assign_encode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     carveout_set = true;
   }
-  assign_encode_kernel<<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(*pyr, prm);
+  assign_encode_kernel<<<dim3((unsigned)batch, (unsigned)tiles), threads, smem, (cudaStream_t)stream>>>(*pyr, prm);
   RN_CUDA_CHECK_LAUNCH("rn_assign_encode");
   return RN_OK;
 }

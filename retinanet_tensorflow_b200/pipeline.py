@@ -60,8 +60,11 @@ class DenseHeadPath(object):
                  anchor_size_mode='tf1_int_trunc', neg_iou=0.4, pos_iou=0.5, focus=2.0, alpha=0.25, eps=1e-7,
                  score_thr=0.5, nms_iou=0.5, max_output_per_class=1000, topk_per_level=0, capacity=4096,
                  out_capacity=None, keep_iou=False, device=None, process_group=None, exchange='auto',
-                 generic_kernels=False):
+                 generic_kernels=False, assign_patch=(0, 0)):
         self.device = _lib.require_cuda(device)
+        # sub-patches (rows, columns) one CTA of the assign kernel handles; (0, 0) = the library's choice.  The
+        # results do not depend on it (tests/test_gpu_assign.py runs several decompositions).
+        self.assign_patch = (int(assign_patch[0]), int(assign_patch[1]))
         self.levels = build_levels() if levels is None else levels
         self.names = list(self.levels)
         self.image_size = (int(image_size[0]), int(image_size[1]))
@@ -293,10 +296,10 @@ class DenseHeadPath(object):
         self._rotate_stats()
         gt_boxes, gt_classes, gt_counts = gt_boxes.contiguous(), gt_classes.contiguous(), gt_counts.contiguous()
         self._stage('assign', lambda: _lib.call(
-            'rn_assign_encode', C.byref(self.pyr), B, _lib.ptr(gt_boxes), _lib.ptr(gt_classes), _lib.ptr(gt_counts),
-            self.max_gt, self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched),
+            'rn_assign_encode_patch', C.byref(self.pyr), B, _lib.ptr(gt_boxes), _lib.ptr(gt_classes),
+            _lib.ptr(gt_counts), self.max_gt, self.num_classes, self.neg_iou, self.pos_iou, C.byref(self._m_matched),
             C.byref(self._m_label), C.byref(self._m_deltas), C.byref(self._m_iou), _lib.ptr(self.stats),
-            _lib.ptr(self.status), _lib.stream_ptr()))
+            _lib.ptr(self.status), self.assign_patch[0], self.assign_patch[1], _lib.stream_ptr()))
         if with_flip:
             st = _lib.stream_ptr()
             none = _lib.Maps()

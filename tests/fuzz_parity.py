@@ -82,8 +82,10 @@ def gpu_assign(case):
     import torch
     from retinanet_tensorflow_b200.pipeline import DenseHeadPath
     n = case['boxes'].shape[0]
+    # the CTA decomposition of the assign kernel varies with the case (results must not depend on it)
+    patch = [(0, 0), (1, 1), (2, 2), (1, 3), (3, 2), (4, 4)][case['seed'] % 6]
     path = DenseHeadPath((case['h'], case['w']), case['c'], 1, n, anchor_size_mode=case['mode'], keep_iou=True,
-                         process_group=False)
+                         process_group=False, assign_patch=patch)
     path.assign(torch.from_numpy(case['boxes'][None]).cuda(), torch.from_numpy(case['classes'][None]).cuda(),
                 torch.tensor([n], dtype=torch.int32).cuda())
     return path.label.cpu().numpy(), path.matched.cpu().numpy(), path.iou_max.cpu().numpy(), path.deltas.cpu().numpy()

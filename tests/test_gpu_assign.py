@@ -46,6 +46,44 @@ def test_assign_encode_matches_oracle(name, batch):
     assert (lab >= 0).sum() > 0 and (lab == -2).sum() > 0  # the case exercises all three states
 
 
+@pytest.mark.parametrize('name,batch', [('voc', 2), ('coco', 1), ('crowded', 1)])
+def test_assign_patch_decomposition_does_not_change_results(name, batch):
+    """rn_assign_encode_patch: one CTA handles sy x sx sub-patches and shares the GT staging and the log-ratio
+    table between them (the table is skipped when too many boxes touch the patch -- crowded).  Every output is
+    bit-identical for every decomposition, including ragged ones that overhang the grid."""
+    from retinanet_tensorflow_b200 import synthetic
+    wl = synthetic.WORKLOADS[name]
+    base = _run_gpu(wl, batch, assign_patch=(1, 1))
+    want = [t.cpu().numpy() for t in (base.matched, base.label, base.iou_max, base.deltas, base.stats)]
+    for patch in [(0, 0), (2, 2), (1, 4), (3, 1), (4, 4), (5, 7), (64, 64)]:
+        path = _run_gpu(wl, batch, assign_patch=patch)
+        got = [t.cpu().numpy() for t in (path.matched, path.label, path.iou_max, path.deltas, path.stats)]
+        for g, w, what in zip(got, want, ('matched', 'label', 'iou_max', 'deltas', 'stats')):
+            np.testing.assert_array_equal(g.view(np.int32) if g.dtype == np.float32 else g,
+                                          w.view(np.int32) if w.dtype == np.float32 else w,
+                                          err_msg='%s with patch %s' % (what, patch))
+
+
+def test_assign_big_batch_takes_the_shared_patch_path_and_matches_small_batches():
+    """A launch that fills the device (automatic 2 x 2 decomposition) gives each image the labels it gets alone."""
+    from retinanet_tensorflow_b200 import synthetic
+    wl = synthetic.WORKLOADS['voc']
+    batch = 48
+    big = _run_gpu(wl, batch)
+    lab = big.label.cpu().numpy()
+    dl = big.deltas.cpu().numpy()
+    one = _run_gpu(wl, 1, first_image=batch - 1, assign_patch=(1, 1))
+    # merged level-major layout: level l holds [B, cells_l * A] rows
+    off_b, off_1 = 0, 0
+    sizes = [int(r) // batch for r in list(big.rows.rows)[:big.rows.num_segments]]
+    for n in sizes:
+        np.testing.assert_array_equal(lab[off_b + (batch - 1) * n: off_b + batch * n], one.label.cpu().numpy()[off_1:off_1 + n])
+        np.testing.assert_array_equal(dl[off_b + (batch - 1) * n: off_b + batch * n].view(np.int32),
+                                      one.deltas.cpu().numpy()[off_1:off_1 + n].view(np.int32))
+        off_b += batch * n
+        off_1 += n
+
+
 def test_assign_float_anchor_size_mode():
     from retinanet_tensorflow_b200 import synthetic
     wl = synthetic.WORKLOADS['shapes']
