@@ -89,6 +89,7 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
   __shared__ float2 s_lut[kLutEntries];
   __shared__ float4 s_shape[RN_MAX_ANCHORS];   // per anchor shape: (h / 2, w / 2, 1 / h, 1 / w)
   __shared__ int s_warp_cnt[32];
+  __shared__ char* s_out[4];   // this image's first row in the level's matched / label / deltas / iou maps
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -121,6 +122,13 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
   const int n_gt = min(max(__ldg(prm.gt_counts + b), 0), prm.max_gt);
   unsigned flags = 0;
   int n_kept = 0;
+  if (tid == 0) {
+    const long long img_row0 = (long long)b * L.grid_h * L.grid_w * A;
+    s_out[0] = reinterpret_cast<char*>(prm.matched.p[l]) + img_row0 * 4;
+    s_out[1] = reinterpret_cast<char*>(prm.label.p[l]) + img_row0 * 4;
+    s_out[2] = reinterpret_cast<char*>(prm.deltas.p[l]) + img_row0 * 16;
+    s_out[3] = prm.iou_max.p[0] ? reinterpret_cast<char*>(prm.iou_max.p[l]) + img_row0 * 4 : nullptr;
+  }
   if (tid < A) {
     const float h = L.anchor_h[tid], w = L.anchor_w[tid];
     // the shifts take a reciprocal (rcp.approx + one Newton step, <= 1 ulp of the quotient); deltas are compared
@@ -201,13 +209,8 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
 
   int n_ign = 0, n_fg = 0;   // both rare: the common warp issues no atomic at all
   if (n_gt == 0 && tid == 0) flags |= RN_FLAG_EMPTY_GT;
-  // (CTA-uniform) this image's rows of the level's maps
-  const long long img_row0 = (long long)b * L.grid_h * L.grid_w * A;
-  int32_t* const out_matched = reinterpret_cast<int32_t*>(prm.matched.p[l]) + img_row0;
-  int32_t* const out_label = reinterpret_cast<int32_t*>(prm.label.p[l]) + img_row0;
-  float4* const out_deltas = reinterpret_cast<float4*>(prm.deltas.p[l]) + img_row0;
-  float* const out_iou = prm.iou_max.p[0] ? reinterpret_cast<float*>(prm.iou_max.p[l]) + img_row0 : nullptr;
   double* const npos = prm.stats ? prm.stats + RN_STAT_NPOS(0) : nullptr;
+  const bool keep_iou = prm.iou_max.p[0] != nullptr;
 
   // (warp-uniform loop bounds: sub-patches and warps that lie outside the grid have nothing to do; there is no CTA
   //  barrier below)
@@ -278,40 +281,47 @@ assign_encode_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_cons
       }
 
       // ---- labels + encoding for the matched box (all anchors, dataset.py:105-121)
-      const int row0 = (cy_i * L.grid_w + cx_i) * A + sub * kApt;
+      if (cell_ok) {
+        const int row0 = (cy_i * L.grid_w + cx_i) * A + sub * kApt;
+        int32_t* const o_matched = reinterpret_cast<int32_t*>(s_out[0]) + row0;
+        int32_t* const o_label = reinterpret_cast<int32_t*>(s_out[1]) + row0;
+        float4* const o_deltas = reinterpret_cast<float4*>(s_out[2]) + row0;
+        float* const o_iou = reinterpret_cast<float*>(s_out[3]) + row0;
 #pragma unroll
-      for (int k = 0; k < kApt; ++k) {
-        const int a = sub * kApt + k;
-        if (cell_ok && a < A) {
-          int lab = RN_LABEL_BACKGROUND;
-          float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-          int matched = -1;
-          if (n_gt > 0) {
-            const int j = bestj[k];
-            matched = s_idx[j];
-            const float4 t = s_ctr[j];   // (cy, cx, h, w) of the matched raw box
-            const bool pos = best[k] >= prm.pos_thr;                 // !bg_mask, dataset.py:83
-            const bool ign = !pos && !(best[k] < prm.neg_thr);       // !trainable_mask, dataset.py:87
-            if (pos) {
-              const int c = s_cls[j];
-              lab = (c >= 0 && c < prm.num_classes) ? c : RN_LABEL_BACKGROUND;  // one_hot of an out-of-range id is 0
-            } else if (ign) {
-              lab = RN_LABEL_IGNORE;
+        for (int k = 0; k < kApt; ++k) {
+          const int a = sub * kApt + k;
+          if (a < A) {
+            int lab = RN_LABEL_BACKGROUND;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            int matched = -1;
+            if (n_gt > 0) {
+              const int j = bestj[k];
+              matched = s_idx[j];
+              const float4 t = s_ctr[j];   // (cy, cx, h, w) of the matched raw box
+              const bool pos = best[k] >= prm.pos_thr;                 // !bg_mask, dataset.py:83
+              const bool ign = !pos && !(best[k] < prm.neg_thr);       // !trainable_mask, dataset.py:87
+              if (pos) {
+                const int c = s_cls[j];
+                lab = (c >= 0 && c < prm.num_classes) ? c : RN_LABEL_BACKGROUND;  // one_hot of an out-of-range id is 0
+              } else if (ign) {
+                lab = RN_LABEL_IGNORE;
+              }
+              const float4 sh = s_shape[a];
+              d.x = fsub(t.x, cy) * sh.z;   // shifts, dataset.py:108
+              d.y = fsub(t.y, cx) * sh.w;
+              const float2 zw = use_lut ? s_lut[j * A + a]
+                                        : log_size_ratios_direct(t.z, t.w, L.anchor_h[a], L.anchor_w[a]);
+              d.z = zw.x;                    // log(scales), dataset.py:110-112
+              d.w = zw.y;
             }
-            const float4 sh = s_shape[a];
-            d.x = fsub(t.x, cy) * sh.z;   // shifts, dataset.py:108
-            d.y = fsub(t.y, cx) * sh.w;
-            const float2 zw = use_lut ? s_lut[j * A + a] : log_size_ratios_direct(t.z, t.w, L.anchor_h[a], L.anchor_w[a]);
-            d.z = zw.x;                    // log(scales), dataset.py:110-112
-            d.w = zw.y;
+            o_matched[k] = matched;
+            o_label[k] = lab;
+            o_deltas[k] = d;
+            if (keep_iou) o_iou[k] = best[k];
+            n_ign += lab == RN_LABEL_IGNORE;
+            n_fg += lab >= 0;
+            if (npos && lab >= 0) atomicAdd(npos + lab, 1.0);
           }
-          out_matched[row0 + k] = matched;
-          out_label[row0 + k] = lab;
-          out_deltas[row0 + k] = d;
-          if (out_iou) out_iou[row0 + k] = best[k];
-          n_ign += lab == RN_LABEL_IGNORE;
-          n_fg += lab >= 0;
-          if (npos && lab >= 0) atomicAdd(npos + lab, 1.0);
         }
       }
     }
