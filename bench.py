@@ -370,7 +370,7 @@ class Harness(object):
 
     def hook_stages(self):
         import torch
-        self.stage_events = {k: [] for k in ('assign', 'cls_sums', 'cls_loss', 'select', 'nms')}
+        self.stage_events = {k: [] for k in ('assign', 'cls_sums', 'cls_loss', 'select', 'nms', 'tail')}
         self.recording = False
 
         def timed(name, fn):
@@ -865,6 +865,7 @@ def run_b200(args):
             'cls_loss': cls_bytes + batch * A * 16,   # + the regression gradient the same launch writes
             'select': None if path.fused_select_supported() else batch * A * 4 * C,  # fused: finalize only
             'nms': None,
+            'tail': None,   # candidate finalize + class-wise NMS in one launch (rn_detect_tail)
         }
         kernels = {}
         for k, v in stage_ms.items():

@@ -431,6 +431,22 @@ RN_API int rn_nms_classwise(int batch, int num_classes, int capacity, const floa
                             int32_t* d_det_classes, int32_t* d_det_index, int32_t* d_det_count,
                             uint32_t* d_status, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The detection tail of a step in ONE launch (one CTA per image): rn_select_finalize (order by anchor, drop
+ * duplicate anchors when dedup != 0, decode / gather the boxes -> d_cand_*, d_cand_count) followed by
+ * rn_nms_classwise on those candidates (-> d_det_*), i.e. utils.boxes_decode + merge_boxes_decoded +
+ * nms_classwise (utils.py:183-227, train.py:68-75) after a select pass (rn_decode_select's first half,
+ * rn_cls_loss_select or rn_head_loss) has left the unordered candidates in d_select_workspace.  Results are
+ * identical to the two separate calls.  Available when rn_detect_tail_supported() != 0 (capacity <= 8192, no
+ * per-level top-k); otherwise call the separate entry points. */
+RN_API int rn_detect_tail_supported(int num_classes, int capacity);
+RN_API int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* regs,
+                          int regs_are_deltas, int capacity, int dedup, float* d_cand_boxes,
+                          float* d_cand_scores, int32_t* d_cand_classes, int32_t* d_cand_anchor,
+                          int32_t* d_cand_count, float iou_thr, int max_output_per_class, int out_capacity,
+                          float* d_det_boxes, float* d_det_scores, int32_t* d_det_classes,
+                          int32_t* d_det_index, int32_t* d_det_count, uint32_t* d_status,
+                          void* d_select_workspace, size_t select_workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

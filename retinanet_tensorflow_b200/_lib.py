@@ -124,6 +124,9 @@ PROTOTYPES = {
     'rn_cls_loss_select': (_i, [_RP, _i, _MP, _MP, _i, _f, _f, _f, _MP, _i, _vp, _vp, _sz, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     'rn_nms_workspace_bytes': (_sz, [_i, _i, _i]),
     'rn_nms_classwise': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'rn_detect_tail_supported': (_i, [_i, _i]),
+    'rn_detect_tail': (_i, [_PP, _i, _i, _MP, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                       _vp, _vp, _sz, _vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -647,6 +647,290 @@ __global__ void __launch_bounds__(256) nms_compact_kernel(const __grid_constant_
   }
 }
 
+// ---- fused detection tail: finalize + class-wise NMS in ONE launch, one CTA per image -----------------------------
+// The tail of a step is latency, not work: ~1-2 k candidates per image, one CTA per image.  The separate kernels
+// (cand_finalize, nms_sort, nms_greedy, nms_compact) pay four launches and sort 12-byte (key, position) pairs with a
+// barrier per bitonic stage.  This kernel keeps everything of one image in shared memory: 64-bit keys that carry
+// their payload in the low bits (no position array), the 2..32 sub-sequences of the bitonic network in registers
+// (warp shuffles, no barrier), order-preserving compaction for the duplicate anchors instead of a second sort, and
+// the per-class greedy pass by the same CTA's warps.  Same ordering rules and the same arithmetic as the separate
+// kernels, which stay for lists longer than kTailMaxCand and for the per-level top-k extension
+// (tests/test_gpu_decode.py compares the two paths bit for bit).
+constexpr int kTailThreads = 1024;
+constexpr int kTailMaxCand = 8192;   // candidates per image (13 index bits in the keys)
+constexpr int kTailIdxBits = 13;
+constexpr int kTailKeptSmem = 40;    // kept boxes per warp staged in shared memory (more: re-read from global)
+constexpr int kTailRounds = kTailMaxCand / kTailThreads;
+
+struct TailParams {
+  Ptrs regs;
+  int regs_are_deltas;
+  int capacity;
+  int dedup;
+  const int32_t* ws_anchor;
+  const float* ws_score;
+  const int32_t* ws_class;
+  float4* cand_boxes;
+  float* cand_scores;
+  int32_t* cand_classes;
+  int32_t* cand_anchor;
+  int32_t* cand_count;   // in: appended, out: final
+  int num_classes, out_capacity, max_out;
+  float iou_thr;
+  float4* det_boxes;
+  float* det_scores;
+  int32_t* det_classes;
+  int32_t* det_index;
+  int32_t* det_count;
+  uint32_t* status;
+};
+
+// CTA-wide bitonic sort of distinct 64-bit keys in shared memory, ascending; n_pad is a power of two >= 32 (padding
+// = ~0).  Strides below 32 run in registers with shuffles; strides >= 32 in shared memory, one pair per thread.
+__device__ void bitonic_sort_u64(unsigned long long* key, unsigned n_pad) {
+  const unsigned lane = threadIdx.x & 31;
+  for (unsigned i = threadIdx.x; i < n_pad; i += blockDim.x) {   // whole warps: n_pad and blockDim are multiples of 32
+    unsigned long long v = key[i];
+#pragma unroll
+    for (unsigned k = 2; k <= 32; k <<= 1) {
+      const bool up = (i & k) == 0;
+#pragma unroll
+      for (unsigned j = k >> 1; j > 0; j >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool take_min = ((lane & j) == 0) == up;
+        v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+      }
+    }
+    key[i] = v;
+  }
+  __syncthreads();
+  for (unsigned k = 64; k <= n_pad; k <<= 1) {
+    for (unsigned j = k >> 1; j >= 32; j >>= 1) {
+      for (unsigned t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+        const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // t with a zero inserted at bit log2(j)
+        const unsigned long long a = key[i], b = key[i | j];
+        if ((a > b) == ((i & k) == 0)) {
+          key[i] = b;
+          key[i | j] = a;
+        }
+      }
+      __syncthreads();
+    }
+    for (unsigned i = threadIdx.x; i < n_pad; i += blockDim.x) {
+      unsigned long long v = key[i];
+      const bool up = (i & k) == 0;
+#pragma unroll
+      for (unsigned j = 16; j > 0; j >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool take_min = ((lane & j) == 0) == up;
+        v = take_min ? (o < v ? o : v) : (o > v ? o : v);
+      }
+      key[i] = v;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1)
+detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ TailParams prm) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = prm.num_classes;
+  const unsigned cap_pad = max(next_pow2((unsigned)min(prm.capacity, kTailMaxCand)), 32u);
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);                   // [cap_pad]
+  NmsBox* s_kbox = reinterpret_cast<NmsBox*>(key + cap_pad);                                    // [32][kTailKeptSmem]
+  int* seg = reinterpret_cast<int*>(s_kbox + (kTailThreads / 32) * kTailKeptSmem);              // [C + 1]
+  int* koff = seg + (C + 1);                                                                    // [C + 1]
+  unsigned short* kept = reinterpret_cast<unsigned short*>(koff + (C + 1));                     // [cap_pad]
+  __shared__ int s_warp[kTailThreads / 32];
+  __shared__ int s_total;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int n_in = min(max(prm.cand_count[b], 0), min(prm.capacity, kTailMaxCand));
+  const size_t base = (size_t)b * prm.capacity;
+  const unsigned idx_mask = (1u << kTailIdxBits) - 1u;
+
+  // ---- 1) ascending anchor index == the reference's (level, y, x, a) order
+  const unsigned n_pad = max(next_pow2((unsigned)n_in), 32u);
+  for (unsigned i = tid; i < n_pad; i += kTailThreads)
+    key[i] = i < (unsigned)n_in ? ((unsigned long long)(unsigned)prm.ws_anchor[base + i] << kTailIdxBits) | i : ~0ull;
+  __syncthreads();
+  bitonic_sort_u64(key, n_pad);
+
+  // ---- 2) duplicate anchors (the fused loss+select pass appends one entry per firing float4 unit): an entry is
+  // dropped when another entry of its anchor beats it (higher probability, then lower class == the first argmax of
+  // utils.py:185-186); 3) ordered outputs + the NMS keys (class asc, score desc, candidate index asc)
+  unsigned long long k2[kTailRounds];
+  int dst[kTailRounds];
+  int done = 0;   // kept entries of earlier rounds (CTA-uniform)
+#pragma unroll
+  for (int r = 0; r < kTailRounds; ++r) {
+    dst[r] = -1;
+    if ((unsigned)(r * kTailThreads) < n_pad) {   // CTA-uniform
+      const int i = r * kTailThreads + tid;
+      bool keep = i < n_in;
+      float si = 0.f;
+      int ci = 0, anchor = 0;
+      if (keep) {
+        const unsigned long long me = key[i];
+        anchor = (int)(me >> kTailIdxBits);
+        si = prm.ws_score[base + (me & idx_mask)];
+        ci = prm.ws_class[base + (me & idx_mask)];
+        if (prm.dedup) {
+          for (int t = i - 1; t >= 0 && (int)(key[t] >> kTailIdxBits) == anchor && keep; --t) {
+            const float st = prm.ws_score[base + (key[t] & idx_mask)];
+            keep = !(st > si || (st == si && prm.ws_class[base + (key[t] & idx_mask)] <= ci));   // an earlier entry also wins full ties
+          }
+          for (int t = i + 1; t < n_in && (int)(key[t] >> kTailIdxBits) == anchor && keep; ++t) {
+            const float st = prm.ws_score[base + (key[t] & idx_mask)];
+            keep = !(st > si || (st == si && prm.ws_class[base + (key[t] & idx_mask)] < ci));
+          }
+        }
+      }
+      // order-preserving compaction: position = kept entries before this one
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_warp[warp] = __popc(m);
+      __syncthreads();
+      int before = done, total = 0;
+#pragma unroll 8
+      for (int w = 0; w < kTailThreads / 32; ++w) {
+        const int c = s_warp[w];
+        before += w < warp ? c : 0;
+        total += c;
+      }
+      __syncthreads();
+      if (keep) {
+        const int o = before + __popc(m & ((1u << lane) - 1u));
+        dst[r] = o;
+        int l = 0;
+        for (int q = 1; q < pyr.num_levels; ++q) l += (anchor >= pyr.level[q].anchor_offset) ? 1 : 0;
+        const rn_level_t& L = pyr.level[l];
+        const int local = anchor - (int)L.anchor_offset;
+        const long long rl = (long long)b * L.grid_h * L.grid_w * L.num_anchors + local;
+        float4 d = __ldg(reinterpret_cast<const float4*>(prm.regs.p[l]) + rl);
+        if (prm.regs_are_deltas) {
+          const int a = local % L.num_anchors;
+          const int cell = local / L.num_anchors;
+          d = decode_one(L, cell / L.grid_w, cell % L.grid_w, a, d);
+        }
+        prm.cand_boxes[base + o] = d;
+        prm.cand_scores[base + o] = si;
+        prm.cand_classes[base + o] = ci;
+        prm.cand_anchor[base + o] = anchor;
+        k2[r] = ((unsigned long long)(unsigned)ci << (32 + kTailIdxBits)) |
+                ((unsigned long long)(~sortable_bits(si)) << kTailIdxBits) | (unsigned)o;
+      }
+      done += total;
+    }
+  }
+  const int n = done;
+  const unsigned n_pad2 = max(next_pow2((unsigned)n), 32u);   // <= n_pad
+  // (every read of the anchor-ordered keys happened before the last barrier of the loop above)
+#pragma unroll
+  for (int r = 0; r < kTailRounds; ++r)
+    if (dst[r] >= 0) key[dst[r]] = k2[r];
+  for (unsigned i = n + tid; i < n_pad2; i += kTailThreads) key[i] = ~0ull;
+  if (tid == 0) prm.cand_count[b] = n;
+  __syncthreads();
+
+  // ---- 4) class-wise NMS (utils.nms_classwise, utils.py:198-210): sort, class segments, greedy pass per class
+  bitonic_sort_u64(key, n_pad2);
+  for (int c = tid; c <= C; c += kTailThreads) {   // class c starts at the first sorted rank whose class >= c
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((unsigned)(key[mid] >> (32 + kTailIdxBits)) < (unsigned)c) lo = mid + 1; else hi = mid;
+    }
+    seg[c] = lo;
+  }
+  __syncthreads();   // (also orders the candidate boxes written above before the reads below)
+  NmsBox* my_kbox = s_kbox + warp * kTailKeptSmem;
+  for (int c = warp; c < C; c += kTailThreads / 32) {
+    const int start = seg[c], end = seg[c + 1];
+    int n_kept = 0;
+    for (int chunk = start; chunk < end && n_kept < prm.max_out; chunk += 32) {
+      const int i = chunk + lane;
+      const bool valid = i < end;
+      NmsBox me = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (valid) me = nms_box(prm.cand_boxes[base + (key[i] & idx_mask)]);
+      bool alive = valid;
+      // against boxes kept by earlier chunks
+      for (int q = 0; q < n_kept && __any_sync(0xffffffffu, alive); ++q) {
+        const NmsBox kb = q < kTailKeptSmem ? my_kbox[q]
+                                            : nms_box(prm.cand_boxes[base + (key[kept[start + q]] & idx_mask)]);
+        if (alive && nms_suppresses(me, kb, prm.iou_thr)) alive = false;
+      }
+      // among the 32 of this chunk, in score order
+      unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+      for (int t = 0; t < 32; ++t) {
+        if (!((alive_mask >> t) & 1u)) continue;  // uniform: alive_mask is warp-wide
+        if (n_kept >= prm.max_out) {
+          alive_mask &= (1u << t) - 1u;           // output full: drop t and everything after it
+          break;
+        }
+        NmsBox kb;
+        kb.y0 = __shfl_sync(0xffffffffu, me.y0, t);
+        kb.x0 = __shfl_sync(0xffffffffu, me.x0, t);
+        kb.y1 = __shfl_sync(0xffffffffu, me.y1, t);
+        kb.x1 = __shfl_sync(0xffffffffu, me.x1, t);
+        kb.area = __shfl_sync(0xffffffffu, me.area, t);
+        if (lane == 0) {
+          if (n_kept < kTailKeptSmem) my_kbox[n_kept] = kb;
+          kept[start + n_kept] = (unsigned short)(chunk + t);
+        }
+        ++n_kept;
+        const bool dies = lane > t && ((alive_mask >> lane) & 1u) && nms_suppresses(me, kb, prm.iou_thr);
+        alive_mask &= ~__ballot_sync(0xffffffffu, dies);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) koff[c] = n_kept;
+  }
+  __syncthreads();
+
+  // ---- 5) class-major compaction of the kept candidates
+  if (warp == 0) {   // exclusive prefix of the per-class counts
+    int carry = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      const int v = c < C ? koff[c] : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      __syncwarp();
+      if (c < C) koff[c] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      koff[C] = carry;
+      s_total = carry;
+    }
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int n_out = min(total, prm.out_capacity);
+  const size_t obase = (size_t)b * prm.out_capacity;
+  for (int o = tid; o < n_out; o += kTailThreads) {   // class by binary search in the prefix
+    int lo = 0, hi = C - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (koff[mid] <= o) lo = mid; else hi = mid - 1;
+    }
+    const unsigned ci = (unsigned)(key[kept[seg[lo] + (o - koff[lo])]] & idx_mask);
+    prm.det_boxes[obase + o] = prm.cand_boxes[base + ci];
+    prm.det_scores[obase + o] = prm.cand_scores[base + ci];
+    prm.det_classes[obase + o] = prm.cand_classes[base + ci];
+    prm.det_index[obase + o] = (int)ci;
+  }
+  if (tid == 0) {
+    if (total > prm.out_capacity && prm.status) atomicOr(prm.status, RN_FLAG_DET_OVERFLOW);
+    prm.det_count[b] = n_out;
+  }
+}
+
 static unsigned host_next_pow2(unsigned v) {
   unsigned p = 2;
   while (p < v) p <<= 1;
@@ -929,5 +1213,77 @@ extern "C" int rn_nms_classwise(int batch, int num_classes, int capacity, const 
   RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(greedy)");
   nms_compact_kernel<<<batch, 256, (size_t)(num_classes + 1) * sizeof(int), st>>>(p);
   RN_CUDA_CHECK_LAUNCH("rn_nms_classwise(compact)");
+  return RN_OK;
+}
+
+static size_t tail_smem_bytes(int num_classes, int capacity) {
+  unsigned pad = host_next_pow2((unsigned)(capacity < kTailMaxCand ? capacity : kTailMaxCand));
+  if (pad < 32) pad = 32;
+  return (size_t)pad * 8 + (size_t)(kTailThreads / 32) * kTailKeptSmem * sizeof(NmsBox) +
+         2 * (size_t)(num_classes + 1) * sizeof(int) + (size_t)pad * 2;
+}
+
+extern "C" int rn_detect_tail_supported(int num_classes, int capacity) {
+  return num_classes >= 1 && num_classes < (1 << 19) && capacity >= 1 && capacity <= kTailMaxCand &&
+         tail_smem_bytes(num_classes, capacity) <= 200 * 1024;
+}
+
+extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* regs,
+                              int regs_are_deltas, int capacity, int dedup, float* d_cand_boxes, float* d_cand_scores,
+                              int32_t* d_cand_classes, int32_t* d_cand_anchor, int32_t* d_cand_count, float iou_thr,
+                              int max_output_per_class, int out_capacity, float* d_det_boxes, float* d_det_scores,
+                              int32_t* d_det_classes, int32_t* d_det_index, int32_t* d_det_count, uint32_t* d_status,
+                              void* d_select_workspace, size_t select_workspace_bytes, void* stream) {
+  RN_REQUIRE(pyr && maps_present(regs), RN_ERR_BAD_ARG, "rn_detect_tail: NULL input");
+  RN_REQUIRE(d_cand_boxes && d_cand_scores && d_cand_classes && d_cand_anchor && d_cand_count && d_select_workspace,
+             RN_ERR_BAD_ARG, "rn_detect_tail: NULL candidate array");
+  RN_REQUIRE(d_det_boxes && d_det_scores && d_det_classes && d_det_index && d_det_count, RN_ERR_BAD_ARG,
+             "rn_detect_tail: NULL output");
+  RN_REQUIRE(batch >= 0 && num_classes >= 1 && capacity >= 1 && out_capacity >= 1 && max_output_per_class >= 0,
+             RN_ERR_BAD_ARG, "rn_detect_tail: bad sizes");
+  RN_REQUIRE(iou_thr >= 0.f && iou_thr <= 1.f, RN_ERR_BAD_ARG, "iou_threshold must be in [0, 1]");
+  RN_REQUIRE(rn_detect_tail_supported(num_classes, capacity), RN_ERR_UNSUPPORTED,
+             "rn_detect_tail: capacity %d / %d classes exceed the one-launch tail (use rn_select_finalize + "
+             "rn_nms_classwise)", capacity, num_classes);
+  RN_REQUIRE(select_workspace_bytes >= rn_select_workspace_bytes(batch, capacity), RN_ERR_CAPACITY,
+             "rn_detect_tail: workspace too small");
+  RN_REQUIRE((((uintptr_t)d_cand_boxes | (uintptr_t)d_det_boxes) & 15) == 0, RN_ERR_BAD_ARG,
+             "box arrays must be 16-byte aligned");
+  if (batch == 0) return RN_OK;
+  for (int l = 0; l < pyr->num_levels; ++l)
+    RN_REQUIRE(regs->p[l] && ((uintptr_t)regs->p[l] & 15) == 0, RN_ERR_BAD_ARG,
+               "regs map of level %d missing or not 16-byte aligned", l);
+  const size_t n = (size_t)batch * capacity;
+  char* ws = (char*)d_select_workspace;
+  TailParams tp;
+  tp.regs = make_ptrs(regs);
+  tp.regs_are_deltas = regs_are_deltas;
+  tp.capacity = capacity;
+  tp.dedup = dedup;
+  tp.ws_anchor = (const int32_t*)ws; ws += align256(n * 4);
+  tp.ws_score = (const float*)ws; ws += align256(n * 4);
+  tp.ws_class = (const int32_t*)ws;
+  tp.cand_boxes = (float4*)d_cand_boxes;
+  tp.cand_scores = d_cand_scores;
+  tp.cand_classes = d_cand_classes;
+  tp.cand_anchor = d_cand_anchor;
+  tp.cand_count = d_cand_count;
+  tp.num_classes = num_classes;
+  tp.out_capacity = out_capacity;
+  tp.max_out = max_output_per_class;
+  tp.iou_thr = iou_thr;
+  tp.det_boxes = (float4*)d_det_boxes;
+  tp.det_scores = d_det_scores;
+  tp.det_classes = d_det_classes;
+  tp.det_index = d_det_index;
+  tp.det_count = d_det_count;
+  tp.status = d_status;
+  static bool tail_opted = false;   // once per process, not per call
+  if (!tail_opted) {
+    cudaFuncSetAttribute(detect_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    tail_opted = true;
+  }
+  detect_tail_kernel<<<batch, kTailThreads, tail_smem_bytes(num_classes, capacity), (cudaStream_t)stream>>>(*pyr, tp);
+  RN_CUDA_CHECK_LAUNCH("rn_detect_tail");
   return RN_OK;
 }

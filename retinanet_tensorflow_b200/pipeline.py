@@ -60,11 +60,13 @@ class DenseHeadPath(object):
                  anchor_size_mode='tf1_int_trunc', neg_iou=0.4, pos_iou=0.5, focus=2.0, alpha=0.25, eps=1e-7,
                  score_thr=0.5, nms_iou=0.5, max_output_per_class=1000, topk_per_level=0, capacity=4096,
                  out_capacity=None, keep_iou=False, device=None, process_group=None, exchange='auto',
-                 generic_kernels=False, assign_patch=(0, 0)):
+                 generic_kernels=False, assign_patch=(0, 0), one_launch_tail=True):
         self.device = _lib.require_cuda(device)
         # sub-patches (rows, columns) one CTA of the assign kernel handles; (0, 0) = the library's choice.  The
         # results do not depend on it (tests/test_gpu_assign.py runs several decompositions).
         self.assign_patch = (int(assign_patch[0]), int(assign_patch[1]))
+        # one_launch_tail=False keeps candidate finalize and NMS as separate launches (the parity tests compare both)
+        self.one_launch_tail = bool(one_launch_tail)
         self.levels = build_levels() if levels is None else levels
         self.names = list(self.levels)
         self.image_size = (int(image_size[0]), int(image_size[1]))
@@ -441,6 +443,27 @@ class DenseHeadPath(object):
             _lib.stream_ptr()))
         return self.cand_count
 
+    def tail_fused_supported(self):
+        """The detection tail (candidate finalize + class-wise NMS) runs as ONE launch when the candidate lists fit
+        the kernel's shared memory and the per-level top-k extension is off (rn_detect_tail)."""
+        return self.one_launch_tail and self.topk_per_level == 0 and \
+            bool(_lib.lib.rn_detect_tail_supported(self.num_classes, self.capacity))
+
+    def detect_tail(self, regression, dedup=True):
+        """select_finalize() + nms() in one launch; same results (tests/test_gpu_decode.py)."""
+        if not self.tail_fused_supported():
+            self.select_finalize(regression)
+            return self.nms()
+        m_reg, _ = self._maps(regression, 4)
+        self._stage('tail', lambda: _lib.call(
+            'rn_detect_tail', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_reg), 1, self.capacity,
+            int(dedup), _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
+            _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), self.nms_iou, self.max_output_per_class,
+            self.out_capacity, _lib.ptr(self.det_boxes), _lib.ptr(self.det_scores), _lib.ptr(self.det_classes),
+            _lib.ptr(self.det_index), _lib.ptr(self.det_count), _lib.ptr(self.status), _lib.ptr(self._sel_ws),
+            self._sel_ws_bytes, _lib.stream_ptr()))
+        return self.det_count
+
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
     def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
         self.join()
@@ -503,8 +526,7 @@ class DenseHeadPath(object):
             self._side_done = None
         if not overlap_detect:
             self.loss_and_select(logits, regression, finalize=False)
-            self.select_finalize(regression)
-            self.nms()
+            self.detect_tail(regression)
             return self.loss_out, self.det_count
         defer = self._multi_rank() and self._can_defer_loss() and not self._static_stats
         self.loss_and_select(logits, regression, finalize=False, defer_loss=defer)
@@ -523,8 +545,7 @@ class DenseHeadPath(object):
             self._side.wait_event(ready)
             if defer:   # loss-sum exchange + finalize: nothing on the main stream waits for them
                 self._finish_loss(stats_now)   # this step's ring vector: not reused before the tail is waited for
-            self.select_finalize(regression)
-            self.nms()
+            self.detect_tail(regression)
             self._side_done = torch.cuda.Event()
             self._side_done.record(self._side)
         return self.loss_out, self.det_count

@@ -208,6 +208,115 @@ def test_overlapped_detection_tail_gives_the_same_results():
     assert torch.equal(path.det_count, want[-1][1]) and torch.equal(path.loss_out, want[-1][0])
 
 
+def _tail_outputs(path, batch):
+    out = {'cand_count': path.cand_count.clone(), 'det_count': path.det_count.clone()}
+    for k in ('cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes'):
+        out[k] = [getattr(path, k)[b, :int(path.cand_count[b])].clone() for b in range(batch)]
+    for k in ('det_index', 'det_boxes', 'det_scores', 'det_classes'):
+        out[k] = [getattr(path, k)[b, :int(path.det_count[b])].clone() for b in range(batch)]
+    return out
+
+
+@pytest.mark.parametrize('name,batch,sigma,kw', [
+    ('voc', 3, 1.0, {}), ('coco', 2, 1.0, {}), ('crowded', 1, 1.0, {}),
+    ('coco', 2, None, {}),                                  # the longest lists that still fit the capacity
+    ('voc', 2, 1.5, {'max_output_per_class': 3}),           # per-class output limit
+    ('voc', 2, 1.5, {'out_capacity': 40}),                  # detection overflow
+])
+def test_one_launch_tail_equals_separate_kernels(name, batch, sigma, kw):
+    """rn_detect_tail (finalize + class-wise NMS in one launch) against rn_select_finalize + rn_nms_classwise on the
+    candidates the fused loss pass left in the workspace: every output bit-identical."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200 import _lib
+    kw = dict({'capacity': 8192}, **kw)
+    wl, path, logits0, regs = _case(name, batch, one_launch_tail=False, **kw)
+    assert path.fused_select_supported() and not path.tail_fused_supported()
+    for sg in ([sigma] if sigma else [1.45, 1.4, 1.35, 1.3, 1.25]):
+        logits = logits0
+        if sg != 1.0:
+            logits, regs = synthetic.head_outputs(path.label, path.deltas, wl.num_classes, seed=5, device='cuda',
+                                                  logit_sigma=sg)
+        lv = logits.view(-1, wl.num_classes)   # several classes of one anchor fire (duplicates to drop), with ties
+        lv[5, 0:3] = torch.tensor([2.0, 3.0, 2.5], device='cuda')
+        if wl.num_classes >= 18:
+            lv[77, 1] = 4.0
+            lv[77, 9] = 4.0
+            lv[77, 17] = 3.0
+        path.status.zero_()
+        path.loss_and_select(logits, regs, finalize=False)
+        path.select_finalize(regs)
+        path.nms()
+        torch.cuda.synchronize()
+        status_want = int(path.status.item())
+        if not status_want & _lib.RN_FLAG_CAND_OVERFLOW:   # (an overflowing list keeps an arbitrary subset)
+            break
+    assert not status_want & _lib.RN_FLAG_CAND_OVERFLOW
+    want = _tail_outputs(path, batch)
+    if sigma is None:
+        assert int(want['cand_count'].max()) > 2048, want['cand_count']
+    for k in ('cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes', 'det_index', 'det_boxes', 'det_scores',
+              'det_classes', 'cand_count', 'det_count', 'status'):
+        getattr(path, k).zero_()
+    path.one_launch_tail = True
+    assert path.tail_fused_supported()
+    path.loss_and_select(logits, regs, finalize=False)
+    path.detect_tail(regs)
+    torch.cuda.synchronize()
+    got = _tail_outputs(path, batch)
+    assert int(path.status.item()) == status_want
+    assert torch.equal(got['cand_count'], want['cand_count']) and torch.equal(got['det_count'], want['det_count'])
+    assert int(want['det_count'].sum()) > 0
+    for k in ('cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes', 'det_index', 'det_boxes', 'det_scores',
+              'det_classes'):
+        for b in range(batch):
+            assert torch.equal(got[k][b], want[k][b]), (k, b)
+
+
+def test_one_launch_tail_after_standalone_select_and_empty_lists():
+    """dedup = 0 (candidates of the standalone select pass) and images without any candidate."""
+    import torch
+    from retinanet_tensorflow_b200 import _lib
+    import ctypes as C
+    wl, path, logits, regs = _case('voc', 2, capacity=4096)
+    logits[: logits.shape[0] // 4] = -20.0      # (merged level-major layout: the first rows are image 0 of P3)
+    path.select(logits, regs)
+    path.nms()
+    torch.cuda.synchronize()
+    want = _tail_outputs(path, 2)
+    # the same select pass again (leaves the workspace as rn_decode_select's first half does), then the fused tail
+    path.select(logits, regs)
+    m_reg, _ = path._maps(regs, 4)
+    for k in ('det_index', 'det_boxes', 'det_count'):
+        getattr(path, k).zero_()
+    # rn_decode_select finalised cand_count in place; the workspace still holds the unordered entries of that count
+    # only when nothing was dropped, which holds without dedup / top-k
+    _lib.call('rn_detect_tail', C.byref(path.pyr), path.batch, path.num_classes, C.byref(m_reg), 1, path.capacity, 0,
+              _lib.ptr(path.cand_boxes), _lib.ptr(path.cand_scores), _lib.ptr(path.cand_classes),
+              _lib.ptr(path.cand_anchor), _lib.ptr(path.cand_count), path.nms_iou, path.max_output_per_class,
+              path.out_capacity, _lib.ptr(path.det_boxes), _lib.ptr(path.det_scores), _lib.ptr(path.det_classes),
+              _lib.ptr(path.det_index), _lib.ptr(path.det_count), _lib.ptr(path.status), _lib.ptr(path._sel_ws),
+              path._sel_ws_bytes, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    got = _tail_outputs(path, 2)
+    for k in want:
+        if k.endswith('count'):
+            assert torch.equal(got[k], want[k]), k
+        else:
+            for b in range(2):
+                assert torch.equal(got[k][b], want[k][b]), (k, b)
+    # no candidates at all
+    path.select(torch.full_like(logits, -20.0), regs)
+    _lib.call('rn_detect_tail', C.byref(path.pyr), path.batch, path.num_classes, C.byref(m_reg), 1, path.capacity, 0,
+              _lib.ptr(path.cand_boxes), _lib.ptr(path.cand_scores), _lib.ptr(path.cand_classes),
+              _lib.ptr(path.cand_anchor), _lib.ptr(path.cand_count), path.nms_iou, path.max_output_per_class,
+              path.out_capacity, _lib.ptr(path.det_boxes), _lib.ptr(path.det_scores), _lib.ptr(path.det_classes),
+              _lib.ptr(path.det_index), _lib.ptr(path.det_count), _lib.ptr(path.status), _lib.ptr(path._sel_ws),
+              path._sel_ws_bytes, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert int(path.cand_count.sum()) == 0 and int(path.det_count.sum()) == 0
+
+
 def test_topk_per_level_prefilter():
     """Extension (not in the reference): k best per (image, level), identity for large k."""
     import torch
