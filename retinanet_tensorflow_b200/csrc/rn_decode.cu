@@ -538,13 +538,25 @@ __device__ __forceinline__ NmsBox nms_box(float4 r) {
   return q;
 }
 
+// iou(a, b) > thr with TF's arithmetic: area <= 0 => IoU 0, intersection = max(dy, 0) * max(dx, 0), IEEE division.
+// Disjoint boxes (most pairs) have intersection 0, hence IoU 0, and 0 > thr is false for every valid threshold --
+// no division.  For the others fl(inter / uni) > thr is decided from inter and thr * uni whenever they differ by more
+// than 2e-6 relative (their roundings are 6e-8 each); only pairs inside that band, and denormal-range
+// intersections, take the division.
 __device__ __forceinline__ bool nms_suppresses(const NmsBox& a, const NmsBox& b, float thr) {
   if (a.area <= 0.f || b.area <= 0.f) return false;
   const float iy0 = fmaxf(a.y0, b.y0), ix0 = fmaxf(a.x0, b.x0);
   const float iy1 = fminf(a.y1, b.y1), ix1 = fminf(a.x1, b.x1);
-  const float inter = fmul(fmaxf(fsub(iy1, iy0), 0.f), fmaxf(fsub(ix1, ix0), 0.f));
-  const float iou = fdiv(inter, fsub(fadd(a.area, b.area), inter));
-  return iou > thr;
+  const float ih = fsub(iy1, iy0), iw = fsub(ix1, ix0);
+  if (!(ih > 0.f && iw > 0.f)) return false;
+  const float inter = fmul(ih, iw);
+  const float uni = fsub(fadd(a.area, b.area), inter);
+  const float rhs = thr * uni;
+  if (inter >= 1e-30f) {
+    if (inter > rhs * 1.000002f) return true;
+    if (inter * 1.000002f < rhs) return false;
+  }
+  return fdiv(inter, uni) > thr;
 }
 
 constexpr int kNmsWarps = 4;
@@ -659,7 +671,8 @@ __global__ void __launch_bounds__(256) nms_compact_kernel(const __grid_constant_
 constexpr int kTailThreads = 1024;
 constexpr int kTailMaxCand = 8192;   // candidates per image (13 index bits in the keys)
 constexpr int kTailIdxBits = 13;
-constexpr int kTailKeptSmem = 40;    // kept boxes per warp staged in shared memory (more: re-read from global)
+constexpr int kTailKeptMin = 40;     // kept boxes per warp staged in shared memory (more: re-read from global);
+constexpr int kTailKeptMax = 256;    // the launch takes as many as fit next to the sort buffers
 constexpr int kTailRounds = kTailMaxCand / kTailThreads;
 
 struct TailParams {
@@ -676,6 +689,7 @@ struct TailParams {
   int32_t* cand_anchor;
   int32_t* cand_count;   // in: appended, out: final
   int num_classes, out_capacity, max_out;
+  int kept_smem;         // kept boxes per warp staged in shared memory
   float iou_thr;
   float4* det_boxes;
   float* det_scores;
@@ -737,18 +751,19 @@ detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_consta
   const int C = prm.num_classes;
   const unsigned cap_pad = max(next_pow2((unsigned)min(prm.capacity, kTailMaxCand)), 32u);
   unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);                   // [cap_pad]
-  NmsBox* s_kbox = reinterpret_cast<NmsBox*>(key + cap_pad);                                    // [32][kTailKeptSmem]
-  int* seg = reinterpret_cast<int*>(s_kbox + (kTailThreads / 32) * kTailKeptSmem);              // [C + 1]
+  NmsBox* s_kbox = reinterpret_cast<NmsBox*>(key + cap_pad);                                    // [32][kept_smem]
+  int* seg = reinterpret_cast<int*>(s_kbox + (kTailThreads / 32) * prm.kept_smem);              // [C + 1]
   int* koff = seg + (C + 1);                                                                    // [C + 1]
   unsigned short* kept = reinterpret_cast<unsigned short*>(koff + (C + 1));                     // [cap_pad]
   __shared__ int s_warp[kTailThreads / 32];
-  __shared__ int s_total;
+  __shared__ int s_total, s_next_class;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const int n_in = min(max(prm.cand_count[b], 0), min(prm.capacity, kTailMaxCand));
   const size_t base = (size_t)b * prm.capacity;
   const unsigned idx_mask = (1u << kTailIdxBits) - 1u;
+  if (tid == 0) s_next_class = 0;
 
   // ---- 1) ascending anchor index == the reference's (level, y, x, a) order
   const unsigned n_pad = max(next_pow2((unsigned)n_in), 32u);
@@ -844,8 +859,12 @@ detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_consta
     seg[c] = lo;
   }
   __syncthreads();   // (also orders the candidate boxes written above before the reads below)
-  NmsBox* my_kbox = s_kbox + warp * kTailKeptSmem;
-  for (int c = warp; c < C; c += kTailThreads / 32) {
+  NmsBox* my_kbox = s_kbox + warp * prm.kept_smem;
+  for (;;) {   // classes are handed out one at a time: their lists differ in length
+    int c = 0;
+    if (lane == 0) c = atomicAdd(&s_next_class, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= C) break;
     const int start = seg[c], end = seg[c + 1];
     int n_kept = 0;
     for (int chunk = start; chunk < end && n_kept < prm.max_out; chunk += 32) {
@@ -856,7 +875,7 @@ detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_consta
       bool alive = valid;
       // against boxes kept by earlier chunks
       for (int q = 0; q < n_kept && __any_sync(0xffffffffu, alive); ++q) {
-        const NmsBox kb = q < kTailKeptSmem ? my_kbox[q]
+        const NmsBox kb = q < prm.kept_smem ? my_kbox[q]
                                             : nms_box(prm.cand_boxes[base + (key[kept[start + q]] & idx_mask)]);
         if (alive && nms_suppresses(me, kb, prm.iou_thr)) alive = false;
       }
@@ -875,7 +894,7 @@ detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_consta
         kb.x1 = __shfl_sync(0xffffffffu, me.x1, t);
         kb.area = __shfl_sync(0xffffffffu, me.area, t);
         if (lane == 0) {
-          if (n_kept < kTailKeptSmem) my_kbox[n_kept] = kb;
+          if (n_kept < prm.kept_smem) my_kbox[n_kept] = kb;
           kept[start + n_kept] = (unsigned short)(chunk + t);
         }
         ++n_kept;
@@ -1216,16 +1235,31 @@ extern "C" int rn_nms_classwise(int batch, int num_classes, int capacity, const 
   return RN_OK;
 }
 
-static size_t tail_smem_bytes(int num_classes, int capacity) {
+static size_t tail_smem_bytes(int num_classes, int capacity, int kept_smem) {
   unsigned pad = host_next_pow2((unsigned)(capacity < kTailMaxCand ? capacity : kTailMaxCand));
   if (pad < 32) pad = 32;
-  return (size_t)pad * 8 + (size_t)(kTailThreads / 32) * kTailKeptSmem * sizeof(NmsBox) +
+  return (size_t)pad * 8 + (size_t)(kTailThreads / 32) * kept_smem * sizeof(NmsBox) +
          2 * (size_t)(num_classes + 1) * sizeof(int) + (size_t)pad * 2;
+}
+
+constexpr size_t kTailSmemLimit = 200 * 1024;
+
+// kept boxes per warp that fit in shared memory beside the sort buffers (no more than a class can keep)
+static int tail_kept_smem(int num_classes, int capacity, int max_out) {
+  int k = kTailKeptMin;
+  const size_t fixed = tail_smem_bytes(num_classes, capacity, 0);
+  if (fixed < kTailSmemLimit) {
+    const size_t room = (kTailSmemLimit - fixed) / ((kTailThreads / 32) * sizeof(NmsBox));
+    if ((size_t)k < room) k = (int)(room < (size_t)kTailKeptMax ? room : (size_t)kTailKeptMax);
+  }
+  const int most = max_out < capacity ? max_out : capacity;
+  if (k > most) k = most > kTailKeptMin ? most : kTailKeptMin;
+  return k;
 }
 
 extern "C" int rn_detect_tail_supported(int num_classes, int capacity) {
   return num_classes >= 1 && num_classes < (1 << 19) && capacity >= 1 && capacity <= kTailMaxCand &&
-         tail_smem_bytes(num_classes, capacity) <= 200 * 1024;
+         tail_smem_bytes(num_classes, capacity, kTailKeptMin) <= kTailSmemLimit;
 }
 
 extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* regs,
@@ -1271,6 +1305,7 @@ extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classe
   tp.num_classes = num_classes;
   tp.out_capacity = out_capacity;
   tp.max_out = max_output_per_class;
+  tp.kept_smem = tail_kept_smem(num_classes, capacity, max_output_per_class);
   tp.iou_thr = iou_thr;
   tp.det_boxes = (float4*)d_det_boxes;
   tp.det_scores = d_det_scores;
@@ -1280,10 +1315,11 @@ extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classe
   tp.status = d_status;
   static bool tail_opted = false;   // once per process, not per call
   if (!tail_opted) {
-    cudaFuncSetAttribute(detect_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(detect_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemLimit);
     tail_opted = true;
   }
-  detect_tail_kernel<<<batch, kTailThreads, tail_smem_bytes(num_classes, capacity), (cudaStream_t)stream>>>(*pyr, tp);
+  detect_tail_kernel<<<batch, kTailThreads, tail_smem_bytes(num_classes, capacity, tp.kept_smem), (cudaStream_t)stream>>>(
+      *pyr, tp);
   RN_CUDA_CHECK_LAUNCH("rn_detect_tail");
   return RN_OK;
 }
