@@ -7,6 +7,7 @@ g.build()"` or `make -C retinanet_tensorflow_b200/csrc`.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import os
 
 RN_MAX_LEVELS = 8
@@ -154,11 +155,17 @@ def call(name, *args):
 
 
 _device_set = {}
+_tls = threading.local()
 
 
 def require_cuda(device=None):
-    """The product path runs on a B200 only."""
+    """The product path runs on a B200 only.  Returns the torch device and makes it the calling thread's current
+    CUDA device for the library (rn_set_device) -- once per thread and device, not per call."""
     import torch
+    if device is None:
+        cached = getattr(_tls, 'current', None)
+        if cached is not None and cached[0] == torch.cuda.current_device():
+            return cached[1]
     if not torch.cuda.is_available():
         raise RuntimeError('retinanet_tensorflow_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -171,7 +178,9 @@ def require_cuda(device=None):
             raise RuntimeError('librndense.so is compiled for sm_100a only; device %d is sm_%d%d' % (idx, *cap))
         _device_set[idx] = True
     call('rn_set_device', idx)
-    return torch.device('cuda', idx)
+    dev = torch.device('cuda', idx)
+    _tls.current = (idx, dev) if idx == torch.cuda.current_device() else None
+    return dev
 
 
 def stream_ptr():

@@ -15,11 +15,29 @@ def level_stride(name):
     return 2 ** int(name[-1])
 
 
+_PYRAMID_CACHE = []   # [(level objects, key, pyramid)]: the per-image drop-in calls ask for the same pyramid again and again
+
+
 def pyramid_for(image_size, levels, anchor_size_mode='tf1_int_trunc', names=None, strides=None):
-    """rn_pyramid_t for an image size and a `Levels`-like mapping (dict order = level order)."""
+    """rn_pyramid_t for an image size and a `Levels`-like mapping (dict order = level order).  The last few
+    results are kept per set of level objects (treated as immutable, like the reference's `build_levels()`
+    result); callers must not modify the returned struct."""
     names = list(levels) if names is None else list(names)
     if strides is None:
         strides = [level_stride(n) for n in names]
+    key = (int(image_size[0]), int(image_size[1]), anchor_size_mode, tuple(names), tuple(int(v) for v in strides))
+    objs = [levels[n] for n in names]
+    for held, k, cached in _PYRAMID_CACHE:
+        if k == key and all(a is b for a, b in zip(held, objs)):
+            return cached
+    pyr = _pyramid_build(image_size, levels, anchor_size_mode, names, strides)
+    _PYRAMID_CACHE.append((objs, key, pyr))   # (list append / slice are atomic under the GIL)
+    if len(_PYRAMID_CACHE) > 16:
+        del _PYRAMID_CACHE[0]
+    return pyr
+
+
+def _pyramid_build(image_size, levels, anchor_size_mode, names, strides):
     sizes = np.ascontiguousarray(np.stack([np.asarray(levels[n].anchor_sizes, np.float64) for n in names], 0))
     if sizes.ndim != 3 or sizes.shape[2] != 2:
         raise ValueError('anchor_sizes must be [A, 2] per level')

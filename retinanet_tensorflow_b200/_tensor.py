@@ -4,6 +4,7 @@ streams only; all arithmetic of the path happens in librndense.so."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -38,10 +39,16 @@ def host_ints(x):
     return [int(v) for v in np.asarray(x).reshape(-1)]
 
 
+@functools.lru_cache(maxsize=64)
+def _flat_pyramid_plain(rows):
+    return pyramid_from_grids([(rows, 1)], np.zeros((1, 1, 2), np.float32))
+
+
 def flat_pyramid(rows, anchor_hw=None):
-    """A one-level pyramid whose `rows` anchors are just rows (geometry unused)."""
-    a = np.zeros((1, 1, 2), np.float32) if anchor_hw is None else np.asarray(anchor_hw, np.float32).reshape(1, -1, 2)
-    return pyramid_from_grids([(max(int(rows), 1), 1)], a)
+    """A one-level pyramid whose `rows` anchors are just rows (geometry unused).  Callers do not modify it."""
+    if anchor_hw is None:
+        return _flat_pyramid_plain(max(int(rows), 1))
+    return pyramid_from_grids([(max(int(rows), 1), 1)], np.asarray(anchor_hw, np.float32).reshape(1, -1, 2))
 
 
 def new_status():

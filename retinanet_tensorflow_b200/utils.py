@@ -168,19 +168,21 @@ def boxes_decode(classifications, regressions, name='boxes_decode', *, score_thr
                             torch.empty((0,), dtype=torch.int64, device=dev))
     pyr = flat_pyramid(rows)
     cap = rows
-    boxes = torch.empty((1, cap, 4), dtype=torch.float32, device=dev)
-    scores = torch.empty((1, cap), dtype=torch.float32, device=dev)
-    classes = torch.empty((1, cap), dtype=torch.int32, device=dev)
-    anchor = torch.empty((1, cap), dtype=torch.int32, device=dev)
-    count = torch.zeros((1,), dtype=torch.int32, device=dev)
-    status = new_status()
+    # one allocation for the four output arrays and the workspace, one zero-fill for (count, status)
     wsb = _lib.lib.rn_select_workspace_bytes(1, cap)
-    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    seg = (16 * cap + 255) & ~255, (4 * cap + 255) & ~255
+    buf = torch.empty((seg[0] + 3 * seg[1] + wsb,), dtype=torch.uint8, device=dev)
+    boxes = buf[:16 * cap].view(torch.float32).view(1, cap, 4)
+    scores = buf[seg[0]:seg[0] + 4 * cap].view(torch.float32).view(1, cap)
+    classes = buf[seg[0] + seg[1]:seg[0] + seg[1] + 4 * cap].view(torch.int32).view(1, cap)
+    anchor = buf[seg[0] + 2 * seg[1]:seg[0] + 2 * seg[1] + 4 * cap].view(torch.int32)
+    ws = buf[seg[0] + 3 * seg[1]:]
+    count_status = torch.zeros((2,), dtype=torch.int32, device=dev)
     _lib.call('rn_decode_select', C.byref(pyr), 1, c, C.byref(_lib.maps_of([classifications.reshape(rows, c)])), 0,
               C.byref(_lib.maps_of([regressions.reshape(rows, 4)])), 0, float(score_threshold), int(topk or 0), cap,
-              _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(classes), _lib.ptr(anchor), _lib.ptr(count),
-              _lib.ptr(status), _lib.ptr(ws), wsb, _lib.stream_ptr())
-    k = int(count.item())
+              _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(classes), _lib.ptr(anchor), _lib.ptr(count_status),
+              C.c_void_p(count_status.data_ptr() + 4), _lib.ptr(ws), wsb, _lib.stream_ptr())
+    k = int(count_status[0].item())   # data-dependent shape, as in the reference: one host read per call
     return BoxesDecoded(boxes=boxes[0, :k], scores=scores[0, :k], class_ids=classes[0, :k].to(torch.int64))
 
 
@@ -198,22 +200,23 @@ def _nms_run(decoded, num_classes, classes_i32, max_output_size, iou_threshold):
     dev = boxes.device
     if n == 0:
         return torch.empty((0,), dtype=torch.int64, device=dev)
-    count = torch.tensor([n], dtype=torch.int32, device=dev)
     ocap = n
-    det_boxes = torch.empty((1, ocap, 4), dtype=torch.float32, device=dev)
-    det_scores = torch.empty((1, ocap), dtype=torch.float32, device=dev)
-    det_classes = torch.empty((1, ocap), dtype=torch.int32, device=dev)
-    det_index = torch.empty((1, ocap), dtype=torch.int32, device=dev)
-    det_count = torch.zeros((1,), dtype=torch.int32, device=dev)
-    status = new_status()
     wsb = _lib.lib.rn_nms_workspace_bytes(1, num_classes, n)
-    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    seg = (16 * ocap + 255) & ~255, (4 * ocap + 255) & ~255
+    buf = torch.empty((seg[0] + 3 * seg[1] + wsb,), dtype=torch.uint8, device=dev)   # outputs + workspace
+    det_boxes = buf[:16 * ocap].view(torch.float32)
+    det_scores = buf[seg[0]:seg[0] + 4 * ocap].view(torch.float32)
+    det_classes = buf[seg[0] + seg[1]:seg[0] + seg[1] + 4 * ocap].view(torch.int32)
+    det_index = buf[seg[0] + 2 * seg[1]:seg[0] + 2 * seg[1] + 4 * ocap].view(torch.int32)
+    ws = buf[seg[0] + 3 * seg[1]:]
+    small = torch.zeros((3,), dtype=torch.int32, device=dev)   # [candidate count, detection count, status]
+    small[0] = n
     _lib.call('rn_nms_classwise', 1, num_classes, n, _lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(classes_i32),
-              _lib.ptr(count), float(iou_threshold), int(max_output_size), ocap, _lib.ptr(det_boxes),
-              _lib.ptr(det_scores), _lib.ptr(det_classes), _lib.ptr(det_index), _lib.ptr(det_count),
-              _lib.ptr(status), _lib.ptr(ws), wsb, _lib.stream_ptr())
-    m = int(det_count.item())
-    return det_index[0, :m].to(torch.int64)
+              _lib.ptr(small), float(iou_threshold), int(max_output_size), ocap, _lib.ptr(det_boxes),
+              _lib.ptr(det_scores), _lib.ptr(det_classes), _lib.ptr(det_index), C.c_void_p(small.data_ptr() + 4),
+              C.c_void_p(small.data_ptr() + 8), _lib.ptr(ws), wsb, _lib.stream_ptr())
+    m = int(small[1].item())
+    return det_index[:m].to(torch.int64)
 
 
 def nms(decoded: BoxesDecoded, max_output_size=NMS_MAX_OUTPUT_SIZE, name='nms', *, iou_threshold=0.5):
@@ -232,13 +235,8 @@ def nms_classwise(decoded: BoxesDecoded, num_classes, name='nms_classwise', *,
     class-major, selection order within a class (utils.py:198-210)."""
     class_ids = as_cuda(decoded.class_ids, None)
     cls32 = class_ids.to(torch.int32)
-    # class ids outside [0, num_classes) never match `tf.equal(class_ids, c)`: drop them
-    valid = (cls32 >= 0) & (cls32 < int(num_classes))
-    if not bool(valid.all()):
-        keep = torch.nonzero(valid).squeeze(1)
-        decoded = BoxesDecoded(as_cuda(decoded.boxes).reshape(-1, 4)[keep], as_cuda(decoded.scores)[keep],
-                               class_ids[keep])
-        class_ids, cls32 = decoded.class_ids, cls32[keep]
+    # class ids outside [0, num_classes) never match `tf.equal(class_ids, c)`: the kernel sorts them behind the last
+    # class segment and never visits them (tests/test_gpu_decode.py), so no host-side filter (and no extra sync)
     idx = _nms_run(decoded, int(num_classes), cls32.contiguous(), max_output_size, iou_threshold)
     return BoxesDecoded(boxes=as_cuda(decoded.boxes).reshape(-1, 4)[idx], scores=as_cuda(decoded.scores)[idx],
                         class_ids=class_ids[idx])

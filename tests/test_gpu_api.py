@@ -189,6 +189,17 @@ def test_boxes_decode_nms_and_classwise_match_oracle():
     np.testing.assert_array_equal(_np(g2.class_ids), w2.class_ids)
     empty = utils.boxes_decode(np.zeros((4, 4, 2, 5), np.float32), boxes[:4, :4, :2])
     assert empty.scores.shape[0] == 0 and utils.nms_classwise(empty, 5).boxes.shape == (0, 4)
+    # class ids outside [0, num_classes) never equal a class in utils.py:201-206: those candidates are dropped
+    odd = want.class_ids.copy()
+    odd[::7] = -1
+    odd[3::11] = 5
+    odd[5::13] = 77
+    g3 = utils.nms_classwise(utils.BoxesDecoded(got.boxes, got.scores, torch.from_numpy(odd).cuda()), num_classes=5)
+    w3 = oracle.nms_classwise(oracle.BoxesDecoded(want.boxes, want.scores, odd), 5)
+    np.testing.assert_array_equal(_np(g3.boxes), w3.boxes)
+    np.testing.assert_array_equal(_np(g3.scores), w3.scores)
+    np.testing.assert_array_equal(_np(g3.class_ids), w3.class_ids)
+    assert w3.scores.shape[0] > 10 and set(np.unique(w3.class_ids)) <= set(range(5))
 
 
 def test_dict_helpers():
