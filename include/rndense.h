@@ -184,8 +184,8 @@ RN_API int rn_assign_encode(const rn_pyramid_t* pyr, int batch, const float* d_g
                             double* d_stats, uint32_t* d_status, void* stream);
 /* Same with an explicit work decomposition: one CTA handles patch_sy x patch_sx sub-patches of 8 x 8 cells and
  * shares the per-image work (GT conversion + culling, encoding table) between them.  0, 0 = automatic (what
- * rn_assign_encode uses: 2 x 2 for launches that fill the device, 1 x 1 otherwise).  The results do not depend on
- * the decomposition; the parity tests run several. */
+ * rn_assign_encode uses: 2 x 2 for launches of many waves, 2 x 1 for medium ones, 1 x 1 for small ones).  The
+ * results do not depend on the decomposition; the parity tests run several. */
 RN_API int rn_assign_encode_patch(const rn_pyramid_t* pyr, int batch, const float* d_gt_boxes,
                                   const int32_t* d_gt_classes, const int32_t* d_gt_counts, int max_gt,
                                   int num_classes, float neg_iou_thr, float pos_iou_thr,

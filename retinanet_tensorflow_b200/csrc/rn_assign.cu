@@ -510,9 +510,11 @@ extern "C" int rn_assign_encode_patch(const rn_pyramid_t* pyr, int batch, const 
   // Small launches keep one sub-patch per CTA so that they still fill the device.
   long long tiles8 = 0;
   for (int l = 0; l < pyr->num_levels; ++l) tiles8 += (long long)pyr->level[l].tiles_x * pyr->level[l].tiles_y;
-  const bool big = tiles8 * batch >= (long long)num_sms() * 32;
-  prm.sy = patch_sy ? patch_sy : (big ? RN_ASSIGN_SUPER_Y : 1);
-  prm.sx = patch_sx ? patch_sx : (big ? RN_ASSIGN_SUPER_X : 1);
+  // (measured: COCO batch 64 -- 24 k sub-patches -- 2 x 2: 0.164 ms, 2 x 1: 0.174, 1 x 1: 0.210; VOC batch 32 -- 3.9 k --
+  //  2 x 1: 0.038 ms, 1 x 1: 0.042, 2 x 2: 0.046)
+  const long long work = tiles8 * batch, sms = num_sms();
+  prm.sy = patch_sy ? patch_sy : (work >= sms * 8 ? RN_ASSIGN_SUPER_Y : 1);
+  prm.sx = patch_sx ? patch_sx : (work >= sms * 32 ? RN_ASSIGN_SUPER_X : 1);
   int tiles = 0;
   for (int l = 0; l < RN_MAX_LEVELS; ++l) {
     prm.tiles_x[l] = 1;
