@@ -57,6 +57,23 @@ def main():
         path.step(*gt, logits + 3.0, regs)
         torch.cuda.synchronize()
         path.check_status(ignore=12)
+    # round 2 (later): assignment with shared CTA patches (ragged decompositions, table and per-anchor encoding) and the
+    # one-launch detection tail (dedup, several classes per anchor, per-class limits)
+    wl = synthetic.Workload('voc16', 2, 200, 264, 16, 70, 3)
+    boxes, cls, counts = synthetic.gt_batch(wl, 3)
+    gt = [torch.from_numpy(v).cuda() for v in (boxes, cls, counts)]
+    for patch, cap, per_class in (((2, 2), 4096, 1000), ((3, 2), 1024, 2), ((1, 1), 8192, 1000)):
+        path = DenseHeadPath((wl.image_h, wl.image_w), 16, 3, wl.max_gt, capacity=cap, max_output_per_class=per_class,
+                             keep_iou=True, process_group=False, assign_patch=patch)
+        path.assign(*gt)
+        logits, regs = synthetic.head_outputs(path.label, path.deltas, 16, seed=6, device='cuda', logit_sigma=1.6)
+        logits.view(-1, 16)[7, 0:9] = 3.0
+        assert path.tail_fused_supported()
+        path.step(*gt, logits, regs)
+        path.step(*gt, logits, regs, overlap_detect=True)
+        path.join()
+        torch.cuda.synchronize()
+        path.check_status(ignore=12)
     b, c = synthetic.gt_for_image(synthetic.WORKLOADS['shapes'], 0)
     dataset.build_labels([128, 160], c, b, build_levels(), 3)
     rng = np.random.default_rng(0)

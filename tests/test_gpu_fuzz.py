@@ -21,3 +21,8 @@ def test_fuzz_loss_slice():
 def test_fuzz_select_slice():
     import fuzz_select
     assert fuzz_select.run(cases=30, seed=1) == 30
+
+
+def test_fuzz_tail_slice():
+    import fuzz_tail
+    assert fuzz_tail.run(cases=30, seed=1) == 30

@@ -1,6 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 {
-timeout 300 python tools/k1_time.py voc,shapes 0x0,1x1,2x1,1x2,2x2 200
-} > gpurun_out/run56.log 2>&1
-tail -30 gpurun_out/run56.log
+timeout 1200 python tests/fuzz_tail.py --cases 800 --seed 5 2>&1 | tail -12
+} > gpurun_out/run58.log 2>&1
+tail -20 gpurun_out/run58.log
