@@ -306,6 +306,15 @@ def ncu_traffic(key):
         return None
 
 
+def ncu_kernels(key):
+    """Pipe utilisation per stage from the committed ncu capture (profiles/ncu_kernels.json), or {}."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_kernels.json')) as f:
+            return json.load(f).get(key) or {}
+    except Exception:
+        return {}
+
+
 def bind_to_gpu_numa_node(dev_index):
     """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned host memory is allocated
     (first touch decides where the pages live; a remote node halves H2D bandwidth on a 2-socket box).
@@ -873,6 +882,9 @@ def run_b200(args):
                 gbs = bytes_per_kernel[k] / (v * 1e-3) / 1e9 if bytes_per_kernel.get(k) else None
                 kernels[k] = {'ms': v, 'alg_GB': (bytes_per_kernel[k] or 0) / 1e9, 'GBps': gbs,
                               'frac_of_hbm': (gbs / peak if gbs else None)}
+        for k, v in ncu_kernels('%s_b%d_%s' % (wl.name, batch, args.cls_mode)).items():
+            if k in kernels and args.logits_dtype == 'f32':
+                kernels[k]['ncu'] = v
         if hz.pipeline and 'assign' in kernels:
             kernels['assign']['note'] = 'runs one step ahead on its own stream, sharing the SMs with the loss kernel'
         achieved = cls_bytes / (stage_ms['cls_loss'] * 1e-3) / 1e9 if stage_ms['cls_loss'] else None

@@ -84,6 +84,34 @@ def test_assign_big_batch_takes_the_shared_patch_path_and_matches_small_batches(
         off_1 += n
 
 
+@pytest.mark.parametrize('aspects,scales', [([(1, 1)], [1]),                                   # A = 1
+                                            ([(1, 2), (1, 1), (2, 1), (1, 3)], [1, 1.26, 1.59, 2.0]),  # A = 16
+                                            ([(1, 2), (2, 1)], [1, 1.3, 1.7, 2.1, 2.6])])              # A = 10
+@pytest.mark.parametrize('patch', [(0, 0), (2, 2), (3, 1)])
+def test_assign_other_anchor_counts(aspects, scales, patch):
+    """Anchor sets other than the reference's 3 x 3 (1, 10 and the maximum of 16 shapes per cell): threads per cell,
+    the per-CTA shape and log-ratio tables and their fall-back (16 shapes x many boxes) against the oracle."""
+    import torch
+    from retinanet_tensorflow_b200 import synthetic
+    from retinanet_tensorflow_b200.pipeline import DenseHeadPath
+    levels = {'P3': oracle.Level(32, aspects, scales), 'P5': oracle.Level(128, aspects, scales)}
+    wl = synthetic.WORKLOADS['voc']
+    batch = 2
+    boxes, classes, counts = synthetic.gt_batch(wl, batch)
+    path = DenseHeadPath((wl.image_h, wl.image_w), wl.num_classes, batch, wl.max_gt, levels=levels, keep_iou=True,
+                         process_group=False, assign_patch=patch)
+    path.assign(torch.from_numpy(boxes).cuda(), torch.from_numpy(classes).cuda(), torch.from_numpy(counts).cuda())
+    torch.cuda.synchronize()
+    path.check_status()
+    ref = helpers.oracle_labels_batch(wl, batch, levels=levels)
+    lab = helpers.compact_labels(helpers.merge_levels(ref['cls'], 1), helpers.merge_levels(ref['mask']))
+    np.testing.assert_array_equal(path.iou_max.cpu().numpy(), helpers.merge_levels(ref['iou']))
+    np.testing.assert_array_equal(path.matched.cpu().numpy(), helpers.merge_levels(ref['idx']).astype(np.int32))
+    np.testing.assert_array_equal(path.label.cpu().numpy(), lab)
+    helpers.assert_close(path.deltas.cpu().numpy(), helpers.merge_levels(ref['reg'], 1), rtol=1e-5, atol=1e-7,
+                         what='deltas')
+
+
 def test_assign_float_anchor_size_mode():
     from retinanet_tensorflow_b200 import synthetic
     wl = synthetic.WORKLOADS['shapes']
