@@ -384,6 +384,8 @@ RN_API size_t rn_select_workspace_bytes(int batch, int capacity);
  *                otherwise they are already corner boxes (pyr may describe geometry only).
  *   topk_per_level > 0: NOT in the reference -- keep the k best of each (image, level)
  *                (ties -> lower anchor), identity when k >= #candidates.
+ *   topk_per_level == -1: select pass only -- the candidates stay unordered in d_workspace and d_cand_count holds the
+ *                appended count; finish with rn_detect_tail (one launch) or rn_select_finalize.
  * Outputs [B, capacity, .]; d_cand_anchor = anchor index within the image; d_cand_count [B]. */
 RN_API int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_classes,
                             const rn_maps_t* scores, int score_format, const rn_maps_t* regs,
@@ -436,12 +438,14 @@ RN_API int rn_nms_classwise(int batch, int num_classes, int capacity, const floa
  * rn_nms_classwise on those candidates (-> d_det_*), i.e. utils.boxes_decode + merge_boxes_decoded +
  * nms_classwise (utils.py:183-227, train.py:68-75) after a select pass (rn_decode_select's first half,
  * rn_cls_loss_select or rn_head_loss) has left the unordered candidates in d_select_workspace.  Results are
- * identical to the two separate calls.  Available when rn_detect_tail_supported() != 0 (capacity <= 8192, no
- * per-level top-k); otherwise call the separate entry points. */
+ * identical to the two separate calls (topk_per_level as in rn_decode_select; 0 = off).  Available when
+ * rn_detect_tail_supported() != 0 (capacity <= 8192); otherwise call the separate entry points.
+ * rn_decode_select(topk_per_level = -1) runs only the select pass and leaves the candidates for this call. */
 RN_API int rn_detect_tail_supported(int num_classes, int capacity);
 RN_API int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* regs,
-                          int regs_are_deltas, int capacity, int dedup, float* d_cand_boxes,
-                          float* d_cand_scores, int32_t* d_cand_classes, int32_t* d_cand_anchor,
+                          int regs_are_deltas, int capacity, int dedup, int topk_per_level,
+                          float* d_cand_boxes, float* d_cand_scores, int32_t* d_cand_classes,
+                          int32_t* d_cand_anchor,
                           int32_t* d_cand_count, float iou_thr, int max_output_per_class, int out_capacity,
                           float* d_det_boxes, float* d_det_scores, int32_t* d_det_classes,
                           int32_t* d_det_index, int32_t* d_det_count, uint32_t* d_status,

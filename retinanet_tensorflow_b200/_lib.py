@@ -126,8 +126,8 @@ PROTOTYPES = {
     'rn_nms_workspace_bytes': (_sz, [_i, _i, _i]),
     'rn_nms_classwise': (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'rn_detect_tail_supported': (_i, [_i, _i]),
-    'rn_detect_tail': (_i, [_PP, _i, _i, _MP, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp,
-                       _vp, _vp, _sz, _vp]),
+    'rn_detect_tail': (_i, [_PP, _i, _i, _MP, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp,
+                       _vp, _vp, _vp, _sz, _vp]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -325,12 +325,14 @@ struct FinalizeParams {
   int32_t* count;             // in: appended, out: final
 };
 
-// Count entries of key[0..n) whose `bit` is clear (CTA-wide); result in every thread.
-__device__ int count_kept(const unsigned long long* key, int n, int bit, int* s_cnt) {
+// Count entries of key[0..n) that carry no drop mark (bits 62 / 63 clear; CTA-wide); result in every thread.
+// (Both marks matter after the top-k pass: the duplicates dropped earlier sort in front of the top-k drops and must
+//  not be counted back in.)
+__device__ int count_kept(const unsigned long long* key, int n, int* s_cnt) {
   if (threadIdx.x == 0) *s_cnt = 0;
   __syncthreads();
   int c = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) c += ((key[i] >> bit) & 1ull) == 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += (key[i] >> 62) == 0;
   c = warp_sum(c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(s_cnt, c);
   __syncthreads();
@@ -397,7 +399,7 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
     }
     if (__syncthreads_or(mine)) {
       bitonic_sort_pairs(key, pos, n_pad);
-      n = count_kept(key, n, 62, &s_cnt);
+      n = count_kept(key, n, &s_cnt);
     }
   }
 
@@ -434,7 +436,7 @@ cand_finalize_kernel(const __grid_constant__ rn_pyramid_t pyr, int batch, const 
     __syncthreads();
     if (any) {
       bitonic_sort_pairs(key, pos, n_pad);
-      n = count_kept(key, n, 63, &s_cnt);
+      n = count_kept(key, n, &s_cnt);
     }
   }
 
@@ -690,6 +692,7 @@ struct TailParams {
   int32_t* cand_count;   // in: appended, out: final
   int num_classes, out_capacity, max_out;
   int kept_smem;         // kept boxes per warp staged in shared memory
+  int topk;              // per-level top-k (extension, not in the reference); 0 = off
   float iou_thr;
   float4* det_boxes;
   float* det_scores;
@@ -745,13 +748,33 @@ __device__ void bitonic_sort_u64(unsigned long long* key, unsigned n_pad) {
   }
 }
 
+// Does entry i of the anchor-ordered keys survive the duplicate-anchor rule?  (The fused loss+select pass appends one
+// entry per firing float4 unit: an entry is dropped when another entry of its anchor beats it -- higher probability,
+// then lower class == the first argmax of utils.py:185-186; an earlier entry also wins full ties.)
+__device__ __forceinline__ bool tail_keeps(const unsigned long long* key, int i, int n_in, size_t base, float si, int ci,
+                                           const TailParams& prm) {
+  const unsigned idx_mask = (1u << kTailIdxBits) - 1u;
+  const int anchor = (int)(key[i] >> kTailIdxBits);
+  bool keep = true;
+  for (int t = i - 1; t >= 0 && (int)(key[t] >> kTailIdxBits) == anchor && keep; --t) {
+    const float st = prm.ws_score[base + (key[t] & idx_mask)];
+    keep = !(st > si || (st == si && prm.ws_class[base + (key[t] & idx_mask)] <= ci));
+  }
+  for (int t = i + 1; t < n_in && (int)(key[t] >> kTailIdxBits) == anchor && keep; ++t) {
+    const float st = prm.ws_score[base + (key[t] & idx_mask)];
+    keep = !(st > si || (st == si && prm.ws_class[base + (key[t] & idx_mask)] < ci));
+  }
+  return keep;
+}
+
 __global__ void __launch_bounds__(kTailThreads, 1)
 detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ TailParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = prm.num_classes;
   const unsigned cap_pad = max(next_pow2((unsigned)min(prm.capacity, kTailMaxCand)), 32u);
   unsigned long long* key = reinterpret_cast<unsigned long long*>(smem_raw);                   // [cap_pad]
-  NmsBox* s_kbox = reinterpret_cast<NmsBox*>(key + cap_pad);                                    // [32][kept_smem]
+  unsigned long long* key2 = key + cap_pad;                                                     // [cap_pad] iff topk > 0
+  NmsBox* s_kbox = reinterpret_cast<NmsBox*>(key2 + (prm.topk > 0 ? cap_pad : 0));              // [32][kept_smem]
   int* seg = reinterpret_cast<int*>(s_kbox + (kTailThreads / 32) * prm.kept_smem);              // [C + 1]
   int* koff = seg + (C + 1);                                                                    // [C + 1]
   unsigned short* kept = reinterpret_cast<unsigned short*>(koff + (C + 1));                     // [cap_pad]
@@ -772,9 +795,54 @@ detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_consta
   __syncthreads();
   bitonic_sort_u64(key, n_pad);
 
-  // ---- 2) duplicate anchors (the fused loss+select pass appends one entry per firing float4 unit): an entry is
-  // dropped when another entry of its anchor beats it (higher probability, then lower class == the first argmax of
-  // utils.py:185-186); 3) ordered outputs + the NMS keys (class asc, score desc, candidate index asc)
+  // ---- 1b) per-level top-k (extension, not in the reference): the survivors are marked first (`kept` is free until
+  // the NMS phase); a level that still holds more than k entries ranks them by (score desc, anchor asc) with one more
+  // sort and drops everything past k
+  unsigned short* flag = kept;
+  if (prm.topk > 0) {
+    for (int i = tid; i < n_in; i += kTailThreads) {
+      bool keep = true;
+      if (prm.dedup) {
+        const unsigned long long me = key[i];
+        keep = tail_keeps(key, i, n_in, base, prm.ws_score[base + (me & idx_mask)], prm.ws_class[base + (me & idx_mask)],
+                          prm);
+      }
+      flag[i] = keep;
+    }
+    __syncthreads();
+    for (int l = 0; l < pyr.num_levels; ++l) {   // CTA-uniform control flow throughout
+      const unsigned lo_a = (unsigned)pyr.level[l].anchor_offset;
+      const unsigned hi_a = l + 1 < pyr.num_levels ? (unsigned)pyr.level[l + 1].anchor_offset
+                                                   : (unsigned)pyr.anchors_per_image;
+      int lo = 0, hi = n_in;
+      while (lo < hi) { const int m = (lo + hi) >> 1; if ((unsigned)(key[m] >> kTailIdxBits) < lo_a) lo = m + 1; else hi = m; }
+      const int start = lo;
+      hi = n_in;
+      while (lo < hi) { const int m = (lo + hi) >> 1; if ((unsigned)(key[m] >> kTailIdxBits) < hi_a) lo = m + 1; else hi = m; }
+      const int end = lo;
+      if (end - start <= prm.topk) continue;
+      int alive = 0;
+      for (int c0 = start; c0 < end; c0 += kTailThreads) {
+        const int i = c0 + tid;
+        alive += __syncthreads_count(i < end && flag[i]);
+      }
+      if (alive <= prm.topk) continue;
+      const unsigned m_pad = max(next_pow2((unsigned)(end - start)), 32u);
+      for (unsigned t = tid; t < m_pad; t += kTailThreads) {
+        const int i = start + (int)t;
+        key2[t] = (i < end && flag[i])
+                      ? ((unsigned long long)(~sortable_bits(prm.ws_score[base + (key[i] & idx_mask)])) << kTailIdxBits) | t
+                      : ~0ull;
+      }
+      __syncthreads();
+      bitonic_sort_u64(key2, m_pad);
+      for (unsigned t = prm.topk + tid; t < (unsigned)alive; t += kTailThreads) flag[start + (int)(key2[t] & idx_mask)] = 0;
+      __syncthreads();
+    }
+  }
+
+  // ---- 2) duplicate anchors dropped (tail_keeps) by an order-preserving compaction; 3) ordered outputs + the NMS
+  // keys (class asc, score desc, candidate index asc)
   unsigned long long k2[kTailRounds];
   int dst[kTailRounds];
   int done = 0;   // kept entries of earlier rounds (CTA-uniform)
@@ -791,16 +859,8 @@ detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_consta
         anchor = (int)(me >> kTailIdxBits);
         si = prm.ws_score[base + (me & idx_mask)];
         ci = prm.ws_class[base + (me & idx_mask)];
-        if (prm.dedup) {
-          for (int t = i - 1; t >= 0 && (int)(key[t] >> kTailIdxBits) == anchor && keep; --t) {
-            const float st = prm.ws_score[base + (key[t] & idx_mask)];
-            keep = !(st > si || (st == si && prm.ws_class[base + (key[t] & idx_mask)] <= ci));   // an earlier entry also wins full ties
-          }
-          for (int t = i + 1; t < n_in && (int)(key[t] >> kTailIdxBits) == anchor && keep; ++t) {
-            const float st = prm.ws_score[base + (key[t] & idx_mask)];
-            keep = !(st > si || (st == si && prm.ws_class[base + (key[t] & idx_mask)] < ci));
-          }
-        }
+        if (prm.topk > 0) keep = flag[i] != 0;
+        else if (prm.dedup) keep = tail_keeps(key, i, n_in, base, si, ci, prm);
       }
       // order-preserving compaction: position = kept entries before this one
       const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -1099,6 +1159,7 @@ extern "C" int rn_decode_select(const rn_pyramid_t* pyr, int batch, int num_clas
   else if (vec4) launch_select_lpr<4>(lpr, upl, (unsigned)blocks, st, segs, sp);
   else launch_select_lpr<1>(lpr, upl, (unsigned)blocks, st, segs, sp);
   RN_CUDA_CHECK_LAUNCH("rn_decode_select(select)");
+  if (topk_per_level < 0) return RN_OK;   // select only: the candidates stay unordered in the workspace
 
   return rn_select_finalize(pyr, batch, regs, regs_are_deltas, topk_per_level, capacity, 0, d_cand_boxes,
                             d_cand_scores, d_cand_classes, d_cand_anchor, d_cand_count, d_workspace, workspace_bytes,
@@ -1235,19 +1296,19 @@ extern "C" int rn_nms_classwise(int batch, int num_classes, int capacity, const 
   return RN_OK;
 }
 
-static size_t tail_smem_bytes(int num_classes, int capacity, int kept_smem) {
+static size_t tail_smem_bytes(int num_classes, int capacity, int kept_smem, bool topk) {
   unsigned pad = host_next_pow2((unsigned)(capacity < kTailMaxCand ? capacity : kTailMaxCand));
   if (pad < 32) pad = 32;
-  return (size_t)pad * 8 + (size_t)(kTailThreads / 32) * kept_smem * sizeof(NmsBox) +
+  return (size_t)pad * 8 * (topk ? 2 : 1) + (size_t)(kTailThreads / 32) * kept_smem * sizeof(NmsBox) +
          2 * (size_t)(num_classes + 1) * sizeof(int) + (size_t)pad * 2;
 }
 
 constexpr size_t kTailSmemLimit = 200 * 1024;
 
 // kept boxes per warp that fit in shared memory beside the sort buffers (no more than a class can keep)
-static int tail_kept_smem(int num_classes, int capacity, int max_out) {
+static int tail_kept_smem(int num_classes, int capacity, int max_out, bool topk) {
   int k = kTailKeptMin;
-  const size_t fixed = tail_smem_bytes(num_classes, capacity, 0);
+  const size_t fixed = tail_smem_bytes(num_classes, capacity, 0, topk);
   if (fixed < kTailSmemLimit) {
     const size_t room = (kTailSmemLimit - fixed) / ((kTailThreads / 32) * sizeof(NmsBox));
     if ((size_t)k < room) k = (int)(room < (size_t)kTailKeptMax ? room : (size_t)kTailKeptMax);
@@ -1259,11 +1320,12 @@ static int tail_kept_smem(int num_classes, int capacity, int max_out) {
 
 extern "C" int rn_detect_tail_supported(int num_classes, int capacity) {
   return num_classes >= 1 && num_classes < (1 << 19) && capacity >= 1 && capacity <= kTailMaxCand &&
-         tail_smem_bytes(num_classes, capacity, kTailKeptMin) <= kTailSmemLimit;
+         tail_smem_bytes(num_classes, capacity, kTailKeptMin, true) <= kTailSmemLimit;
 }
 
 extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classes, const rn_maps_t* regs,
-                              int regs_are_deltas, int capacity, int dedup, float* d_cand_boxes, float* d_cand_scores,
+                              int regs_are_deltas, int capacity, int dedup, int topk_per_level, float* d_cand_boxes,
+                              float* d_cand_scores,
                               int32_t* d_cand_classes, int32_t* d_cand_anchor, int32_t* d_cand_count, float iou_thr,
                               int max_output_per_class, int out_capacity, float* d_det_boxes, float* d_det_scores,
                               int32_t* d_det_classes, int32_t* d_det_index, int32_t* d_det_count, uint32_t* d_status,
@@ -1273,7 +1335,8 @@ extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classe
              RN_ERR_BAD_ARG, "rn_detect_tail: NULL candidate array");
   RN_REQUIRE(d_det_boxes && d_det_scores && d_det_classes && d_det_index && d_det_count, RN_ERR_BAD_ARG,
              "rn_detect_tail: NULL output");
-  RN_REQUIRE(batch >= 0 && num_classes >= 1 && capacity >= 1 && out_capacity >= 1 && max_output_per_class >= 0,
+  RN_REQUIRE(batch >= 0 && num_classes >= 1 && capacity >= 1 && out_capacity >= 1 && max_output_per_class >= 0 &&
+                 topk_per_level >= 0,
              RN_ERR_BAD_ARG, "rn_detect_tail: bad sizes");
   RN_REQUIRE(iou_thr >= 0.f && iou_thr <= 1.f, RN_ERR_BAD_ARG, "iou_threshold must be in [0, 1]");
   RN_REQUIRE(rn_detect_tail_supported(num_classes, capacity), RN_ERR_UNSUPPORTED,
@@ -1305,7 +1368,8 @@ extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classe
   tp.num_classes = num_classes;
   tp.out_capacity = out_capacity;
   tp.max_out = max_output_per_class;
-  tp.kept_smem = tail_kept_smem(num_classes, capacity, max_output_per_class);
+  tp.topk = topk_per_level;
+  tp.kept_smem = tail_kept_smem(num_classes, capacity, max_output_per_class, topk_per_level > 0);
   tp.iou_thr = iou_thr;
   tp.det_boxes = (float4*)d_det_boxes;
   tp.det_scores = d_det_scores;
@@ -1318,8 +1382,8 @@ extern "C" int rn_detect_tail(const rn_pyramid_t* pyr, int batch, int num_classe
     cudaFuncSetAttribute(detect_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemLimit);
     tail_opted = true;
   }
-  detect_tail_kernel<<<batch, kTailThreads, tail_smem_bytes(num_classes, capacity, tp.kept_smem), (cudaStream_t)stream>>>(
-      *pyr, tp);
+  detect_tail_kernel<<<batch, kTailThreads, tail_smem_bytes(num_classes, capacity, tp.kept_smem, topk_per_level > 0),
+                       (cudaStream_t)stream>>>(*pyr, tp);
   RN_CUDA_CHECK_LAUNCH("rn_detect_tail");
   return RN_OK;
 }

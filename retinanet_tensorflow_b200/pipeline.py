@@ -445,19 +445,18 @@ class DenseHeadPath(object):
 
     def tail_fused_supported(self):
         """The detection tail (candidate finalize + class-wise NMS) runs as ONE launch when the candidate lists fit
-        the kernel's shared memory and the per-level top-k extension is off (rn_detect_tail)."""
-        return self.one_launch_tail and self.topk_per_level == 0 and \
-            bool(_lib.lib.rn_detect_tail_supported(self.num_classes, self.capacity))
+        the kernel's shared memory (rn_detect_tail: capacity <= 8192)."""
+        return self.one_launch_tail and bool(_lib.lib.rn_detect_tail_supported(self.num_classes, self.capacity))
 
-    def detect_tail(self, regression, dedup=True):
+    def detect_tail(self, regression, dedup=True, regs_are_deltas=True):
         """select_finalize() + nms() in one launch; same results (tests/test_gpu_decode.py)."""
         if not self.tail_fused_supported():
             self.select_finalize(regression)
             return self.nms()
         m_reg, _ = self._maps(regression, 4)
         self._stage('tail', lambda: _lib.call(
-            'rn_detect_tail', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_reg), 1, self.capacity,
-            int(dedup), _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
+            'rn_detect_tail', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_reg), int(regs_are_deltas),
+            self.capacity, int(dedup), self.topk_per_level, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
             _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), self.nms_iou, self.max_output_per_class,
             self.out_capacity, _lib.ptr(self.det_boxes), _lib.ptr(self.det_scores), _lib.ptr(self.det_classes),
             _lib.ptr(self.det_index), _lib.ptr(self.det_count), _lib.ptr(self.status), _lib.ptr(self._sel_ws),
@@ -465,7 +464,9 @@ class DenseHeadPath(object):
         return self.det_count
 
     # ---- stage 3: decode + select + class-wise NMS (utils.boxes_decode + nms_classwise) -----
-    def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
+    def select(self, scores, regression, scores_are_logits=True, regs_are_deltas=True, finalize=True):
+        """Candidates of utils.boxes_decode over all levels.  finalize=False runs only the select pass and leaves the
+        candidates unordered in the workspace (finish with detect_tail(dedup=False))."""
         self.join()
         m_scores, scores_t = self._maps(scores, self.num_classes, self._LOGIT_DTYPES)
         first = scores_t[0] if isinstance(scores_t, (list, tuple)) else scores_t
@@ -474,7 +475,7 @@ class DenseHeadPath(object):
         m_reg, _ = self._maps(regression, 4)
         self._stage('select', lambda: _lib.call(
             'rn_decode_select', C.byref(self.pyr), self.batch, self.num_classes, C.byref(m_scores),
-            fmt, C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level,
+            fmt, C.byref(m_reg), int(regs_are_deltas), self.score_thr, self.topk_per_level if finalize else -1,
             self.capacity, _lib.ptr(self.cand_boxes), _lib.ptr(self.cand_scores), _lib.ptr(self.cand_classes),
             _lib.ptr(self.cand_anchor), _lib.ptr(self.cand_count), _lib.ptr(self.status), _lib.ptr(self._sel_ws),
             self._sel_ws_bytes, _lib.stream_ptr()))
@@ -491,8 +492,14 @@ class DenseHeadPath(object):
         return self.det_count
 
     def detect(self, scores, regression, scores_are_logits=True, regs_are_deltas=True):
-        self.select(scores, regression, scores_are_logits, regs_are_deltas)
-        self.nms()
+        """Inference post-processing: select pass over the scores + ONE launch for ordering, optional per-level top-k,
+        box decoding and class-wise NMS (separate launches where the one-launch tail does not apply)."""
+        if self.tail_fused_supported():
+            self.select(scores, regression, scores_are_logits, regs_are_deltas, finalize=False)
+            self.detect_tail(regression, dedup=False, regs_are_deltas=regs_are_deltas)
+        else:
+            self.select(scores, regression, scores_are_logits, regs_are_deltas)
+            self.nms()
         return self.det_boxes, self.det_scores, self.det_classes, self.det_count
 
     # ---- one whole step of the hot path -----------------------------------------------------

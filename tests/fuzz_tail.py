@@ -1,6 +1,6 @@
 """Randomised fuzz of the one-launch detection tail (GPU): rn_detect_tail against rn_select_finalize +
 rn_nms_classwise on the candidates the fused loss pass leaves in the workspace, for random image sizes,
-class counts, thresholds, capacities, per-class / total output limits and logit distributions (sparse and
+class counts, thresholds, capacities, per-level top-k, per-class / total output limits and logit distributions (sparse and
 dense firing, several classes per anchor, exact score ties).
 
     python tests/fuzz_tail.py --cases 200 --seed 0        # on a GPU box
@@ -48,10 +48,11 @@ def run_case(seed):
     ocap = int(rng.choice([cap, cap, 50]))
     nms_iou = float(rng.choice([0.5, 0.5, 0.0, 0.3, 1.0]))
     spread = float(rng.choice([0.05, 0.2, 0.6]))
-    desc = 'seed=%d %dx%d C=%d B=%d thr=%.2f cap=%d mu=%.1f sigma=%.1f per_class=%d ocap=%d iou=%.1f spread=%.2f' % (
-        seed, h, w, c, batch, thr, cap, mu, sigma, per_class, ocap, nms_iou, spread)
+    topk = int(rng.choice([0, 0, 5, 60, 1000]))
+    desc = 'seed=%d %dx%d C=%d B=%d thr=%.2f cap=%d mu=%.1f sigma=%.1f per_class=%d ocap=%d iou=%.1f spread=%.2f topk=%d' % (
+        seed, h, w, c, batch, thr, cap, mu, sigma, per_class, ocap, nms_iou, spread, topk)
     path = DenseHeadPath((h, w), c, batch, 4, score_thr=thr, capacity=cap, out_capacity=ocap, nms_iou=nms_iou,
-                         max_output_per_class=per_class, process_group=False, one_launch_tail=False)
+                         max_output_per_class=per_class, topk_per_level=topk, process_group=False, one_launch_tail=False)
     gt_boxes = np.zeros((batch, 4, 4), np.float32)
     gt_boxes[:, 0] = [0.2, 0.2, 0.7, 0.8]
     path.assign(torch.from_numpy(gt_boxes).cuda(), torch.zeros((batch, 4), dtype=torch.int32, device='cuda'),

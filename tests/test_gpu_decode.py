@@ -222,6 +222,8 @@ def _tail_outputs(path, batch):
     ('coco', 2, None, {}),                                  # the longest lists that still fit the capacity
     ('voc', 2, 1.5, {'max_output_per_class': 3}),           # per-class output limit
     ('voc', 2, 1.5, {'out_capacity': 40}),                  # detection overflow
+    ('voc', 2, 1.5, {'topk_per_level': 25}),                # per-level top-k (extension): levels above k are ranked
+    ('coco', 1, 1.3, {'topk_per_level': 1000}),             # ... BASELINE config 4's k, P3 above it
 ])
 def test_one_launch_tail_equals_separate_kernels(name, batch, sigma, kw):
     """rn_detect_tail (finalize + class-wise NMS in one launch) against rn_select_finalize + rn_nms_classwise on the
@@ -291,7 +293,7 @@ def test_one_launch_tail_after_standalone_select_and_empty_lists():
         getattr(path, k).zero_()
     # rn_decode_select finalised cand_count in place; the workspace still holds the unordered entries of that count
     # only when nothing was dropped, which holds without dedup / top-k
-    _lib.call('rn_detect_tail', C.byref(path.pyr), path.batch, path.num_classes, C.byref(m_reg), 1, path.capacity, 0,
+    _lib.call('rn_detect_tail', C.byref(path.pyr), path.batch, path.num_classes, C.byref(m_reg), 1, path.capacity, 0, 0,
               _lib.ptr(path.cand_boxes), _lib.ptr(path.cand_scores), _lib.ptr(path.cand_classes),
               _lib.ptr(path.cand_anchor), _lib.ptr(path.cand_count), path.nms_iou, path.max_output_per_class,
               path.out_capacity, _lib.ptr(path.det_boxes), _lib.ptr(path.det_scores), _lib.ptr(path.det_classes),
@@ -307,7 +309,7 @@ def test_one_launch_tail_after_standalone_select_and_empty_lists():
                 assert torch.equal(got[k][b], want[k][b]), (k, b)
     # no candidates at all
     path.select(torch.full_like(logits, -20.0), regs)
-    _lib.call('rn_detect_tail', C.byref(path.pyr), path.batch, path.num_classes, C.byref(m_reg), 1, path.capacity, 0,
+    _lib.call('rn_detect_tail', C.byref(path.pyr), path.batch, path.num_classes, C.byref(m_reg), 1, path.capacity, 0, 0,
               _lib.ptr(path.cand_boxes), _lib.ptr(path.cand_scores), _lib.ptr(path.cand_classes),
               _lib.ptr(path.cand_anchor), _lib.ptr(path.cand_count), path.nms_iou, path.max_output_per_class,
               path.out_capacity, _lib.ptr(path.det_boxes), _lib.ptr(path.det_scores), _lib.ptr(path.det_classes),
@@ -315,6 +317,35 @@ def test_one_launch_tail_after_standalone_select_and_empty_lists():
               path._sel_ws_bytes, _lib.stream_ptr())
     torch.cuda.synchronize()
     assert int(path.cand_count.sum()) == 0 and int(path.det_count.sum()) == 0
+
+
+@pytest.mark.parametrize('topk', [0, 30, 1000])
+def test_detect_one_launch_tail_equals_separate_kernels(topk):
+    """DenseHeadPath.detect (inference post-processing): select pass + rn_detect_tail against select + finalize + the
+    three NMS launches, with and without the per-level top-k."""
+    import torch
+    wl, path, logits, regs = _case('voc', 3, capacity=8192, topk_per_level=topk, one_launch_tail=False)
+    logits = logits + 1.5     # more candidates than k on the fine levels
+    path.detect(logits, regs)
+    torch.cuda.synchronize()
+    want = _tail_outputs(path, 3)
+    for k in ('cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes', 'det_index', 'det_boxes', 'det_scores',
+              'det_classes', 'cand_count', 'det_count'):
+        getattr(path, k).zero_()
+    path.one_launch_tail = True
+    assert path.tail_fused_supported()
+    path.detect(logits, regs)
+    torch.cuda.synchronize()
+    path.check_status()
+    got = _tail_outputs(path, 3)
+    assert torch.equal(got['cand_count'], want['cand_count']) and torch.equal(got['det_count'], want['det_count'])
+    assert int(want['det_count'].sum()) > 0
+    if topk == 30:
+        assert int(want['cand_count'].max()) <= 5 * 30
+    for k in ('cand_anchor', 'cand_scores', 'cand_classes', 'cand_boxes', 'det_index', 'det_boxes', 'det_scores',
+              'det_classes'):
+        for b in range(3):
+            assert torch.equal(got[k][b], want[k][b]), (k, b)
 
 
 def test_topk_per_level_prefilter():
