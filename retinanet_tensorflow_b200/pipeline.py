@@ -524,8 +524,7 @@ class DenseHeadPath(object):
         if not (fused and self.fused_select_supported()):
             self.join()
             self.loss(logits, regression)
-            self.select(logits, regression)
-            self.nms()
+            self.detect(logits, regression)   # select pass + one-launch tail (or the separate launches)
             return self.loss_out, self.det_count
         main = torch.cuda.current_stream()
         if self._side_done is not None:
