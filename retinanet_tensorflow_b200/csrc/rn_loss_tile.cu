@@ -23,6 +23,7 @@
 #include <cmath>
 
 #include "rn_loss_math.cuh"
+#include <type_traits>
 #include "rn_loss_tile.cuh"
 
 namespace rn {
@@ -565,11 +566,15 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
       const unsigned tile_units = nrows * cv;
       float2 acc = f2(0.f);
 
+      // (a full tile -- all but the last tile of a level -- gives every thread all of its units: that copy of the
+      //  loop carries no bounds checks)
+      auto units_of_tile = [&](auto full_c) {
+      constexpr bool kFull = decltype(full_c)::value;
 #pragma unroll
       for (int k = 0; k < kUnitsPerThread; ++k) {
         const unsigned i = threadIdx.x + (unsigned)k * kConsumerThreads;
-        if ((unsigned)warp * 32u + (unsigned)k * kConsumerThreads >= tile_units) break;   // warp-uniform
-        const bool valid = i < tile_units;
+        if (!kFull && (unsigned)warp * 32u + (unsigned)k * kConsumerThreads >= tile_units) break;   // warp-uniform
+        const bool valid = kFull || i < tile_units;
         const unsigned r = geo[k] & 0xffffu, c4 = geo[k] >> 16;
         Unit raw = make_uint4(0, 0, 0, 0);
         if (valid) raw = xs[i];
@@ -626,6 +631,13 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
           if (qcount >= 32u) drain(32u);
         }
       }
+      };
+#ifdef RN_TILE_NO_FULL   // (tuning builds: the one-copy form)
+      units_of_tile(std::false_type{});
+#else
+      if (tile_units == (unsigned)kUnitsPerThread * kConsumerThreads) units_of_tile(std::true_type{});
+      else units_of_tile(std::false_type{});
+#endif
       fx_neg += to_fix(acc.x + acc.y);
 
       if (!DENSE && prm.huber) {
