@@ -562,12 +562,14 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
       const Unit* xs = reinterpret_cast<const Unit*>(st);
       const Unit* zs = reinterpret_cast<const Unit*>(st + prm.x_bytes);          // DENSE
       const int32_t* labs = reinterpret_cast<const int32_t*>(st + prm.x_bytes);  // compact
-      Unit* gout = reinterpret_cast<Unit*>(prm.dlogits.p[s]) + (size_t)row0 * cv;
+      // this thread's first gradient unit of the tile; its other units sit at fixed distances (immediate offsets)
+      Unit* gmine = reinterpret_cast<Unit*>(prm.dlogits.p[s]) + ((size_t)row0 * cv + threadIdx.x);
+      asm volatile("" : "+l"(gmine));   // (the compiler would otherwise redo the 64-bit address per unit)
       const unsigned tile_units = nrows * cv;
       float2 acc = f2(0.f);
 
       // (a full tile -- all but the last tile of a level -- gives every thread all of its units: that copy of the
-      //  loop carries no bounds checks)
+      //  loop carries no bounds checks and, being the training path, no "gradient wanted?" test either)
       auto units_of_tile = [&](auto full_c) {
       constexpr bool kFull = decltype(full_c)::value;
 #pragma unroll
@@ -616,7 +618,7 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
         a2.x = counts ? a2.x : 0.0f;
         a2.y = counts ? a2.y : 0.0f;
         acc = add2(acc, a2);
-        if (plain && write_grad) __stcs(gout + i, outv);
+        if (plain && (kFull || write_grad)) __stcs(gmine + k * kConsumerThreads, outv);
         const unsigned m = __ballot_sync(0xffffffffu, valid && !plain);
         if (m) {
           if (valid && !plain) {
@@ -635,7 +637,7 @@ cls_tile_kernel(const __grid_constant__ Segs segs, const __grid_constant__ TileD
 #ifdef RN_TILE_NO_FULL   // (tuning builds: the one-copy form)
       units_of_tile(std::false_type{});
 #else
-      if (tile_units == (unsigned)kUnitsPerThread * kConsumerThreads) units_of_tile(std::true_type{});
+      if (tile_units == (unsigned)kUnitsPerThread * kConsumerThreads && write_grad) units_of_tile(std::true_type{});
       else units_of_tile(std::false_type{});
 #endif
       fx_neg += to_fix(acc.x + acc.y);
