@@ -118,6 +118,47 @@ def test_rows_and_maps_helpers():
     assert maps.p[0] == 1 << 20 and maps.p[1] == (1 << 20) + 3 * 9 * 63 * 63 * 16
 
 
+def test_new_entry_points_validate_their_arguments():
+    """rn_assign_encode_patch / rn_detect_tail reject bad arguments before touching the device (status codes, no
+    launch), and the capability query follows the documented limits."""
+    from retinanet_tensorflow_b200 import _lib
+    from retinanet_tensorflow_b200._pyramid import pyramid_for
+    from retinanet_tensorflow_b200.levels import build_levels
+    pyr = pyramid_for((500, 500), build_levels())
+    lib = _lib.lib
+    assert lib.rn_detect_tail_supported(80, 8192) == 1 and lib.rn_detect_tail_supported(80, 8193) == 0
+    assert lib.rn_detect_tail_supported(0, 100) == 0 and lib.rn_detect_tail_supported(3, 1) == 1
+    m = _lib.Maps()
+    # NULL maps / arrays
+    assert lib.rn_detect_tail(C.byref(pyr), 1, 3, C.byref(m), 1, 64, 1, 0, None, None, None, None, None, 0.5, 10, 64, None,
+                              None, None, None, None, None, None, 0, None) == -1
+    assert b'rn_detect_tail' in lib.rn_last_error()
+    # patch shape: both zero or both in 1..64
+    for sy, sx in ((0, 2), (2, 0), (-1, 1), (65, 1)):
+        assert lib.rn_assign_encode_patch(C.byref(pyr), 1, None, None, None, 4, 3, 0.4, 0.5, C.byref(m), C.byref(m),
+                                          C.byref(m), C.byref(m), None, None, sy, sx, None) == -1
+        assert b'patch_sy' in lib.rn_last_error()
+
+
+def test_pyramid_cache_keys_on_levels_size_and_mode():
+    """The drop-in modules ask for the same rn_pyramid_t once per image: the host keeps the last few, keyed on the
+    level objects (identity), the image size, the anchor-size mode, names and strides."""
+    from retinanet_tensorflow_b200._pyramid import pyramid_for
+    from retinanet_tensorflow_b200.levels import build_levels
+    la, lb = build_levels(), build_levels()
+    p1 = pyramid_for((500, 667), la)
+    assert pyramid_for((500, 667), la) is p1
+    assert pyramid_for([500, 667], la, names=list(la)) is p1
+    assert pyramid_for((500, 667), lb) is not p1                      # other level objects
+    assert pyramid_for((500, 668), la) is not p1                      # other image size
+    pf = pyramid_for((500, 667), la, 'float')
+    assert pf is not p1 and pf.level[0].anchor_h[0] != p1.level[0].anchor_h[0]
+    one = pyramid_for((500, 667), {'L': la['P4']}, 'tf1_int_trunc', ['L'], [16])
+    assert one.num_levels == 1 and one.level[0].grid_h == 32 and one is not p1
+    assert pyramid_for((500, 667), {'L': la['P4']}, 'tf1_int_trunc', ['L'], [16]) is one   # same level object, new dict
+    assert pyramid_for((500, 667), {'L': la['P4']}, 'tf1_int_trunc', ['L'], [8]) is not one
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
