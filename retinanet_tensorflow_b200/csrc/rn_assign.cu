@@ -11,7 +11,7 @@
 // boxes instead of being evaluated per anchor.  Anchors are regenerated in registers (never read from memory); each
 // thread scans the staged boxes for its anchors with the reference's float32 op sequence (no FMA contraction, IEEE
 // division).  Round 2 profile of the one-sub-patch form (profiles/r02_k1_breakdown.md): 1327 instructions per warp
-// of which only 27 % were the IoU scan -- 37 % were per-CTA fixed cost and 31 % the per-anchor encoding.
+// of which only 29 % were the IoU scan -- 37 % were per-CTA fixed cost and 31 % the per-anchor encoding.
 #include "rn_common.cuh"
 #include "rn_tiles.cuh"
 
@@ -69,8 +69,8 @@ __device__ __noinline__ float2 log_size_ratios_direct(float th, float tw, float 
   return log_size_ratios(th, tw, h, w);
 }
 
-// 64 registers (no spills): five 192-thread CTAs per SM.  The compiler's own choice (80) leaves four and is 8 % slower,
-// 56 spills into the scan loop (profiles/r02_k1_breakdown.md).
+// 64 registers (one 12-byte spill): five 192-thread CTAs per SM.  The compiler's own choice (80) leaves four and is
+// 8 % slower, 56 spills into the scan loop (profiles/r02_k1_breakdown.md).
 #ifndef RN_ASSIGN_MAXREG
 #define RN_ASSIGN_MAXREG 64
 #endif
