@@ -19,7 +19,10 @@ namespace rn {
 
 constexpr int kApt = 3;          // anchors per thread
 constexpr int kMaxGtSmem = 2048; // GT boxes per image the assign kernel can stage
-constexpr int kLutEntries = 576; // (staged GT + 1) x anchors-per-cell table of log size ratios (else: per anchor)
+#ifndef RN_ASSIGN_LUT
+#define RN_ASSIGN_LUT 576
+#endif
+constexpr int kLutEntries = RN_ASSIGN_LUT;   // (staged GT + 1) x anchors-per-cell table of log size ratios (else: per anchor)
 
 #ifndef RN_ASSIGN_SUPER_Y
 #define RN_ASSIGN_SUPER_Y 2
