@@ -767,7 +767,13 @@ __device__ __forceinline__ bool tail_keeps(const unsigned long long* key, int i,
   return keep;
 }
 
-__global__ void __launch_bounds__(kTailThreads, 1)
+// 32 registers (two CTAs' worth per SM; a 40-byte spill outside the loops): the tail runs beside the next step's
+// assignment kernel, and with half of an SM's registers per CTA that kernel's CTAs share the 64 SMs the tail sits on
+// (assignment in the step 0.214 -> 0.203 ms, tail unchanged; profiles/r02_tail.md).
+#ifndef RN_TAIL_MINB
+#define RN_TAIL_MINB 2
+#endif
+__global__ void __launch_bounds__(kTailThreads, RN_TAIL_MINB)
 detect_tail_kernel(const __grid_constant__ rn_pyramid_t pyr, const __grid_constant__ TailParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = prm.num_classes;
